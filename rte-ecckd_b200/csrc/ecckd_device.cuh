@@ -1,0 +1,146 @@
+// ecckd_device.cuh -- device-side model description and the per-(column,layer)
+// index arithmetic shared by every kernel.
+//
+// The index arithmetic restates /root/reference/src/gas_optics_ecckd.f90:104-107,
+// 120-163 and :271-280 operation by operation with the round-to-nearest
+// intrinsics (__dadd_rn, __dmul_rn, __ddiv_rn), which nvcc never contracts into
+// FMAs: apart from log() (CUDA's vs libm's, both < 1 ulp) every intermediate is
+// the IEEE value the Fortran computes, so ip0/it0/iv0 are bit-exact.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ecckd {
+
+constexpr int kMaxGases = 16;  // gas_optics_ecckd.f90:24
+constexpr int kMaxBil = 8;     // bilinear (code 0/1/3) gases the walking kernel keeps in registers
+
+enum Code : int { kNone = 0, kLinear = 1, kLut = 2, kRelLinear = 3 };  // :54-57
+
+// Device-resident packed tables (one copy per GPU, read-only after create).
+struct DevModel {
+    int ngpt, np, nt, nplanck;
+    double logp0;      // log_pressure(1)                              :104
+    double dlogp;      // log_pressure(2) - log_pressure(1)            :105
+    double dt;         // temperature(1,2) - temperature(1,1)          :106
+    double gw;         // 1./(gravity*0.001*dry_air_molar_mass)        :107 (default-real literals)
+    double p_clamp;    // size(log_pressure) - 1.0001_wp               :125
+    double t_clamp;    // size(temperature,2) - 1.0001_wp              :137
+    double tp0, dtp;   // temperature_planck(1), (2)-(1)               :271-272
+    double pi;         // (double)3.14159265359f                       :53
+    const double *tbase;     // temperature(:,1)                       :131-132
+    const float *k32;        // all coefficient tables, fp32 (exact)   element (g,p,t,v) of a gas at
+    const double *k64;       //   off + g + ngpt*(p + np*(t + nt*v)), 0-based
+    const float *planck32;   // planck_function(ngpt, nplanck)
+    const double *planck64;
+    const double *rayleigh;  // (ngpt)
+    const double *solar;     // (ngpt)
+};
+
+// One active gas of this call, already resolved against the model on the host
+// (gas_optical_depth, :348-374): caller order, unknown names dropped, composite once.
+struct GasRef {
+    const void *vmr;
+    long long col_stride, lay_stride;  // elements of Real
+    long long table_off;               // element offset of coefficient(1,1,1,1)
+    double ref;                        // reference_mole_fraction          :146
+    double mf0;                        // mole_fraction(1)                 :153
+    double log_mf0;                    // log(mole_fraction(1))            :156
+    double dlog_mf;                    // log(mole_fraction(2)/mole_fraction(1))  :154-155
+    double v_clamp;                    // size(mole_fraction) - 1.001_wp   :160
+    int code;
+    int nv;
+};
+
+struct CallGases {
+    int n;
+    int nbil;               // number of code 0/1/3 gases
+    int lut;                // index in g[] of the (single) LUT gas, or -1
+    int bil[kMaxBil];       // indices in g[] of the bilinear gases, caller order
+    GasRef g[kMaxGases];
+};
+
+template <typename Real> struct TableOf;
+template <> struct TableOf<double> {
+    __device__ static const double *k(const DevModel &m) { return m.k64; }
+    __device__ static const double *planck(const DevModel &m) { return m.planck64; }
+};
+template <> struct TableOf<float> {
+    __device__ static const float *k(const DevModel &m) { return m.k32; }
+    __device__ static const float *planck(const DevModel &m) { return m.planck32; }
+};
+
+// ---- per-cell interpolation state (pressure, temperature) -------------------
+struct CellIndex {
+    int ip0, it0;      // 1-based, as in the reference
+    double pw1, tw1;   // pressure_weight1, temperature_weight1
+    double sw;         // simple_weight = global_weight*(plev(j+1)-plev(j))   :143
+};
+
+__device__ __forceinline__ CellIndex cell_index(const DevModel &m, double p_upper, double p_lower, double tlay)
+{
+    // p_upper = level_pressure(i,j), p_lower = level_pressure(i,j+1)
+    CellIndex c;
+    double lp = log(__dmul_rn(0.5, __dadd_rn(p_lower, p_upper)));                     // :120
+    double x = __ddiv_rn(__dsub_rn(lp, m.logp0), m.dlogp);                            // :121
+    x = __dadd_rn(1.0, fmax(0.0, fmin(x, m.p_clamp)));                                // :122-125
+    c.ip0 = __double2int_rz(x);                                                       // :126
+    c.pw1 = __dsub_rn(x, (double)c.ip0);
+    double pw0 = __dsub_rn(1.0, c.pw1);
+    double t0 = __dadd_rn(__dmul_rn(pw0, m.tbase[c.ip0 - 1]), __dmul_rn(c.pw1, m.tbase[c.ip0]));  // :131-132
+    double y = __ddiv_rn(__dsub_rn(tlay, t0), m.dt);                                  // :133
+    y = __dadd_rn(1.0, fmax(0.0, fmin(y, m.t_clamp)));                                // :134-137
+    c.it0 = __double2int_rz(y);                                                       // :138
+    c.tw1 = __dsub_rn(y, (double)c.it0);
+    c.sw = __dmul_rn(m.gw, __dsub_rn(p_lower, p_upper));                              // :143
+    return c;
+}
+
+// weight of one gas (:144-149; code 0 uses simple_weight, :216)
+__device__ __forceinline__ double gas_weight(const GasRef &g, double sw, double vmr)
+{
+    if (g.code == kRelLinear) return __dmul_rn(sw, __dsub_rn(vmr, g.ref));
+    if (g.code == kNone) return sw;
+    return __dmul_rn(sw, vmr);
+}
+
+// look-up-table index in mole fraction (:153-163); returns 1-based iv0, sets vw1
+__device__ __forceinline__ int vmr_index(const GasRef &g, double vmr, double &vw1)
+{
+    double lv = log(fmax(vmr, g.mf0));                                                // :153
+    double z = __ddiv_rn(__dsub_rn(lv, g.log_mf0), g.dlog_mf);                        // :156
+    z = __dadd_rn(1.0, fmax(0.0, fmin(z, g.v_clamp)));                                // :157-160
+    int iv0 = __double2int_rz(z);                                                     // :161
+    vw1 = __dsub_rn(z, (double)iv0);
+    return iv0;
+}
+
+// Planck LUT index (:275-284).  Returns 1-based it0 (0 = the T < T_planck(1)
+// branch); a0/a1 are the factors of planck_function(:,max(it0,1)) and (:,+1)
+// BEFORE the division by pi: in range (w0, w1); below range (T/t0, 0).
+__device__ __forceinline__ int planck_index(const DevModel &m, double T, double &a0, double &a1)
+{
+    double x = __ddiv_rn(__dsub_rn(T, m.tp0), m.dtp);                                 // :275
+    if (x >= 0.0) {
+        x = __dadd_rn(1.0, x);                                                        // :277
+        int it0 = min(__double2int_rz(x), m.nplanck - 1);                             // :278
+        a1 = __dsub_rn(x, (double)it0);                                               // :279
+        a0 = __dsub_rn(1.0, a1);                                                      // :280
+        return it0;
+    }
+    a0 = __ddiv_rn(T, m.tp0);                                                         // :284
+    a1 = 0.0;
+    return 0;
+}
+
+template <typename Real>
+__device__ __forceinline__ double load_vmr(const GasRef &g, long long col, long long lay)
+{
+    return (double)static_cast<const Real *>(g.vmr)[col * g.col_stride + lay * g.lay_stride];
+}
+
+// streaming (evict-first) store: outputs are written once and never re-read here,
+// keep them from displacing the L2-resident tables
+template <typename Real> __device__ __forceinline__ void store_cs(Real *p, Real v) { __stcs(p, v); }
+
+}  // namespace ecckd

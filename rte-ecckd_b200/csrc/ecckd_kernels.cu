@@ -1,0 +1,429 @@
+// ecckd_kernels.cu -- sm_100a kernels of the ECCKD gas-optics hot path.
+//
+// Replaces the loop nests of /root/reference/src/gas_optics_ecckd.f90:
+//   calculate_optical_depth :117-240 (once per gas) + accumulate :370
+//   calculate_planck_function :273-288 (x3) + shifted copies :423-424
+//   calculate_rayleigh_optical_depth :313-317 + ssa/g :456-460 + toa_src :468-472
+// with ONE fused pass per call: interpolation indices once per (column, layer),
+// all gases accumulated in registers, every output element stored exactly once.
+//
+// Two kernels:
+//   walk_kernel    -- the product path.  One warp walks one column top to bottom,
+//                     lanes = g-points.  Lane-distributed index arithmetic (lane l
+//                     does layer j0+l, results broadcast through shared memory),
+//                     coefficient corner rows cached in registers and reloaded
+//                     only when (ip0,it0[,iv0]) move, results transposed through a
+//                     padded shared-memory tile so global stores are full 128-byte
+//                     column-contiguous lines.
+//   generic_kernel -- thread per (column, layer), loop over g; handles any gas mix
+//                     (several LUT gases, >8 bilinear gases, tables with negative
+//                     entries) with the reference's per-g clamp.  Also the
+//                     cross-check of walk_kernel in the GPU tests.
+#include "ecckd_device.cuh"
+#include "ecckd_kernels.h"
+
+namespace ecckd {
+
+// ============================================================================
+// generic kernel
+// ============================================================================
+template <typename Real, bool SW>
+__global__ void __launch_bounds__(256)
+generic_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
+               const __grid_constant__ KernelArgs<Real> a)
+{
+    const long long ncell = (long long)a.ncol * a.nlay;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncell) return;
+    const long long col = idx % a.ncol, lay = idx / a.ncol;
+    const int ngpt = m.ngpt, np = m.np, nt = m.nt;
+    const long long ncol = a.ncol, nlay = a.nlay;
+    const Real *ktab = TableOf<Real>::k(m);
+
+    const double pu = (double)a.plev[col + ncol * lay], pl = (double)a.plev[col + ncol * (lay + 1)];
+    const CellIndex ci = cell_index(m, pu, pl, (double)a.tlay[col + ncol * lay]);
+    const Real pw1 = (Real)ci.pw1, pw0 = (Real)__dsub_rn(1.0, ci.pw1);
+    const Real tw1 = (Real)ci.tw1, tw0 = (Real)__dsub_rn(1.0, ci.tw1);
+    const long long s_t = (long long)ngpt * np, s_v = s_t * nt;
+    const long long corner = (long long)ngpt * (ci.ip0 - 1) + s_t * (ci.it0 - 1);
+
+    // per-gas weights and LUT indices, once per cell
+    Real w[kMaxGases], vw1[kMaxGases];
+    long long base[kMaxGases];
+    for (int q = 0; q < cg.n; ++q) {
+        const GasRef &gr = cg.g[q];
+        double vmr = gr.code == kNone ? 0.0 : load_vmr<Real>(gr, col, lay);
+        w[q] = (Real)gas_weight(gr, ci.sw, vmr);
+        base[q] = gr.table_off + corner;
+        vw1[q] = 0;
+        if (gr.code == kLut) {
+            double v1;
+            int iv0 = vmr_index(gr, vmr, v1);
+            vw1[q] = (Real)v1;
+            base[q] += s_v * (iv0 - 1);
+        }
+    }
+
+    // Planck factors (LW)
+    Real a_lay0 = 0, a_lay1 = 0, a_up0 = 0, a_up1 = 0, a_dn0 = 0, a_dn1 = 0;
+    int r_lay = 0, r_up = 0, r_dn = 0;
+    const Real *ptab = TableOf<Real>::planck(m);
+    if (!SW) {
+        double a0, a1;
+        int it = planck_index(m, (double)a.tlay[col + ncol * lay], a0, a1);
+        r_lay = max(it, 1) - 1; a_lay0 = (Real)a0; a_lay1 = (Real)a1;
+        if (a.tlev) {
+            it = planck_index(m, (double)a.tlev[col + ncol * lay], a0, a1);
+            r_up = max(it, 1) - 1; a_up0 = (Real)a0; a_up1 = (Real)a1;
+            it = planck_index(m, (double)a.tlev[col + ncol * (lay + 1)], a0, a1);
+            r_dn = max(it, 1) - 1; a_dn0 = (Real)a0; a_dn1 = (Real)a1;
+        }
+    }
+    const Real pi = (Real)m.pi;
+
+    for (int g = 0; g < ngpt; ++g) {
+        Real tau = 0;
+        for (int q = 0; q < cg.n; ++q) {
+            const Real *k = ktab + base[q] + g;
+            // :198-203 / :216-221 grouping
+            Real od = tw0 * (pw0 * k[0] + pw1 * k[ngpt]) + tw1 * (pw0 * k[s_t] + pw1 * k[s_t + ngpt]);
+            if (cg.g[q].code == kLut) {
+                const Real *k2 = k + s_v;                                              // :167-178
+                Real od1 = tw0 * (pw0 * k2[0] + pw1 * k2[ngpt]) + tw1 * (pw0 * k2[s_t] + pw1 * k2[s_t + ngpt]);
+                od = ((Real)1 - vw1[q]) * od + vw1[q] * od1;
+            }
+            od = w[q] * od;
+            if (od < (Real)0) od = 0;                                                  // :233-238
+            tau += od;                                                                 // :370
+        }
+        const long long o = col + ncol * (lay + nlay * g);
+        if (SW) {
+            const Real ray = (Real)ci.sw * (Real)m.rayleigh[g];                        // :313-316
+            tau += ray;                                                                // :456
+            store_cs(a.out[0] + o, tau);
+            if (a.out[1]) store_cs(a.out[1] + o, ray / tau);                           // :459
+            if (a.out[2]) store_cs(a.out[2] + o, (Real)0);                             // :460
+        } else {
+            store_cs(a.out[0] + o, tau);
+            store_cs(a.out[1] + o, (a_lay0 * ptab[r_lay * ngpt + g] + a_lay1 * ptab[(r_lay + 1) * ngpt + g]) / pi);
+            if (a.tlev) {
+                store_cs(a.out[2] + o, (a_dn0 * ptab[r_dn * ngpt + g] + a_dn1 * ptab[(r_dn + 1) * ngpt + g]) / pi); // :423
+                store_cs(a.out[3] + o, (a_up0 * ptab[r_up * ngpt + g] + a_up1 * ptab[(r_up + 1) * ngpt + g]) / pi); // :424
+            }
+        }
+    }
+    if (lay == 0) {
+        if (SW) {
+            if (a.out2d)
+                for (int g = 0; g < ngpt; ++g) a.out2d[col + ncol * g] = (Real)m.solar[g];      // :468-472
+        } else {
+            double a0, a1;
+            int it = planck_index(m, (double)a.tsfc[col], a0, a1);                               // :408-412
+            const int r = max(it, 1) - 1;
+            for (int g = 0; g < ngpt; ++g)
+                a.out2d[col + ncol * g] = ((Real)a0 * ptab[r * ngpt + g] + (Real)a1 * ptab[(r + 1) * ngpt + g]) / pi;
+        }
+    }
+}
+
+// ============================================================================
+// column-walking kernel
+// ============================================================================
+// Per-(warp, layer) record produced by the lane-distributed index phase and read
+// back as warp-wide broadcasts.
+template <typename Real> struct alignas(16) Rec {
+    Real c[4];          // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
+    Real w[kMaxBil];    // weight of each bilinear gas
+    Real wl, vw1;       // LUT gas: weight, vmr_weight1
+    Real pa[4];         // LW: lay (a0,a1)/pi, lower level (a0,a1)/pi.  SW: pa[0] = moles_per_layer
+    int ip, it, iv, prow;   // 0-based corner indices; prow = lay_row | lev_row << 16
+};
+
+template <typename Real, bool SW, int TC, int L>
+__global__ void __launch_bounds__(TC * 32, 1)
+walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
+            const __grid_constant__ KernelArgs<Real> a)
+{
+    constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled at write-out
+    constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Rec<Real> *recs = reinterpret_cast<Rec<Real> *>(smem_raw);
+    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(Rec<Real>) * TC * 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ncol = a.ncol, nlay = a.nlay;
+    const long long col0 = (long long)blockIdx.x * TC;
+    const long long col = col0 + warp;
+    const bool col_ok = col < ncol;
+    const int ngpt = m.ngpt, np = m.np;
+    const int g0 = blockIdx.y * 32;
+    const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
+    const Real *ktab = TableOf<Real>::k(m) + g;
+    const Real *ptab = TableOf<Real>::planck(m) + g;
+    const long long s_t = (long long)ngpt * np, s_v = s_t * m.nt;
+    const int nbil = cg.nbil;
+    const bool has_lut = cg.lut >= 0;
+    const long long lut_off = has_lut ? cg.g[cg.lut].table_off : 0;
+
+    Real kb[kMaxBil][4];
+    Real kh[8];
+#pragma unroll
+    for (int b = 0; b < kMaxBil; ++b) kb[b][0] = kb[b][1] = kb[b][2] = kb[b][3] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kh[i] = 0;
+    int cur_ip = -2, cur_it = -2, cur_hp = -2, cur_ht = -2, cur_hv = -2;
+
+    const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
+    Real lev_prev = 0;   // Planck source at the upper level of the current layer
+    if (!SW && col_ok && a.tlev) {
+        double a0, a1;
+        const int it = planck_index(m, (double)a.tlev[col], a0, a1);
+        const int r = max(it, 1) - 1;
+        lev_prev = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
+    }
+
+    int buf = 0;
+    for (long long j0 = 0; j0 < nlay; j0 += 32) {
+        // ---- phase A: lane l computes the record of layer j0 + l ----------------
+        __syncwarp();
+        {
+            const long long j = j0 + lane;
+            if (col_ok && j < nlay) {
+                Rec<Real> r;
+                const double pu = (double)a.plev[col + ncol * j], pl = (double)a.plev[col + ncol * (j + 1)];
+                const double tl = (double)a.tlay[col + ncol * j];
+                const CellIndex ci = cell_index(m, pu, pl, tl);
+                const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
+                r.c[0] = (Real)(tw0 * pw0); r.c[1] = (Real)(tw0 * ci.pw1);
+                r.c[2] = (Real)(ci.tw1 * pw0); r.c[3] = (Real)(ci.tw1 * ci.pw1);
+                r.ip = ci.ip0 - 1; r.it = ci.it0 - 1; r.iv = 0; r.prow = 0;
+#pragma unroll
+                for (int b = 0; b < kMaxBil; ++b) {
+                    Real wv = 0;
+                    if (b < nbil) {
+                        const GasRef &gr = cg.g[cg.bil[b]];
+                        const double vmr = gr.code == kNone ? 0.0 : load_vmr<Real>(gr, col, j);
+                        wv = (Real)gas_weight(gr, ci.sw, vmr);
+                    }
+                    r.w[b] = wv;
+                }
+                r.wl = 0; r.vw1 = 0;
+                if (has_lut) {
+                    const GasRef &gr = cg.g[cg.lut];
+                    const double vmr = load_vmr<Real>(gr, col, j);
+                    double v1;
+                    r.iv = vmr_index(gr, vmr, v1) - 1;
+                    r.vw1 = (Real)v1;
+                    r.wl = (Real)gas_weight(gr, ci.sw, vmr);
+                }
+                r.pa[0] = r.pa[1] = r.pa[2] = r.pa[3] = 0;
+                if (SW) {
+                    r.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
+                } else {
+                    double a0, a1;
+                    int it = planck_index(m, tl, a0, a1);
+                    int rows = max(it, 1) - 1;
+                    r.pa[0] = (Real)__ddiv_rn(a0, m.pi); r.pa[1] = (Real)__ddiv_rn(a1, m.pi);
+                    if (a.tlev) {
+                        it = planck_index(m, (double)a.tlev[col + ncol * (j + 1)], a0, a1);
+                        rows |= (max(it, 1) - 1) << 16;
+                        r.pa[2] = (Real)__ddiv_rn(a0, m.pi); r.pa[3] = (Real)__ddiv_rn(a1, m.pi);
+                    }
+                    r.prow = rows;
+                }
+                recs[warp * 32 + lane] = r;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase B: walk the (up to) 32 layers of this chunk ------------------
+        const int nl_chunk = (int)min((long long)32, nlay - j0);
+        for (int l = 0; l < nl_chunk; ++l) {
+            const long long j = j0 + l;
+            const int ls = (int)(j % L);
+            if (col_ok) {
+                const Rec<Real> &r = recs[warp * 32 + l];
+                const int ip = r.ip, it = r.it;
+                if (ip != cur_ip || it != cur_it) {
+                    const bool shift = (ip == cur_ip + 1) && (it == cur_it);
+                    const Real *corner = ktab + (long long)ngpt * ip + s_t * it;
+#pragma unroll
+                    for (int b = 0; b < kMaxBil; ++b) {
+                        if (b < nbil) {
+                            const Real *k = corner + cg.g[cg.bil[b]].table_off;
+                            if (shift) { kb[b][0] = kb[b][1]; kb[b][2] = kb[b][3]; }
+                            else { kb[b][0] = k[0]; kb[b][2] = k[s_t]; }
+                            kb[b][1] = k[ngpt]; kb[b][3] = k[s_t + ngpt];
+                        }
+                    }
+                    cur_ip = ip; cur_it = it;
+                }
+                Real tau = 0;
+                if (has_lut) {
+                    const int iv = r.iv;
+                    if (ip != cur_hp || it != cur_ht || iv != cur_hv) {
+                        const Real *k = ktab + lut_off + (long long)ngpt * ip + s_t * it + s_v * iv;
+                        kh[0] = k[0]; kh[1] = k[ngpt]; kh[2] = k[s_t]; kh[3] = k[s_t + ngpt];
+                        k += s_v;
+                        kh[4] = k[0]; kh[5] = k[ngpt]; kh[6] = k[s_t]; kh[7] = k[s_t + ngpt];
+                        cur_hp = ip; cur_ht = it; cur_hv = iv;
+                    }
+                    const Real wl = r.wl;
+                    if (!(wl < (Real)0)) {
+                        const Real b0 = r.c[0] * kh[0] + r.c[1] * kh[1] + r.c[2] * kh[2] + r.c[3] * kh[3];
+                        const Real b1 = r.c[0] * kh[4] + r.c[1] * kh[5] + r.c[2] * kh[6] + r.c[3] * kh[7];
+                        const Real v1 = r.vw1;
+                        tau = wl * (((Real)1 - v1) * b0 + v1 * b1);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < kMaxBil; ++b) {
+                    if (b < nbil) {
+                        const Real wv = r.w[b];
+                        // tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the
+                        // per-g clamp (:233-238) is a warp-uniform skip
+                        if (!(wv < (Real)0)) {
+                            const Real bil = r.c[0] * kb[b][0] + r.c[1] * kb[b][1] + r.c[2] * kb[b][2] + r.c[3] * kb[b][3];
+                            tau += wv * bil;
+                        }
+                    }
+                }
+                Real *st = stage + (size_t)buf * NOUT * L * 32 * TCP + (size_t)ls * 32 * TCP + lane * TCP + warp;
+                if (SW) {
+                    const Real ray = r.pa[0] * sigma;               // :313-316
+                    tau += ray;                                     // :456
+                    st[0] = tau;
+                    st[(size_t)L * 32 * TCP] = ray / tau;           // :459
+                } else {
+                    const int rl = r.prow & 0xffff, rv = r.prow >> 16;
+                    const Real lay_src = r.pa[0] * ptab[rl * ngpt] + r.pa[1] * ptab[(rl + 1) * ngpt];
+                    const Real lev_next = r.pa[2] * ptab[rv * ngpt] + r.pa[3] * ptab[(rv + 1) * ngpt];
+                    st[0] = tau;
+                    st[(size_t)1 * L * 32 * TCP] = lay_src;
+                    st[(size_t)2 * L * 32 * TCP] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
+                    st[(size_t)3 * L * 32 * TCP] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
+                    lev_prev = lev_next;
+                }
+            }
+            if (ls == L - 1 || j == nlay - 1) {
+                __syncthreads();
+                const int nl = ls + 1;
+                const long long lay0 = j - ls;
+                const Real *sb = stage + (size_t)buf * NOUT * L * 32 * TCP;
+#pragma unroll
+                for (int it2 = 0; it2 < NOUT * L; ++it2) {
+                    const int idx = it2 * (TC * 32) + threadIdx.x;
+                    const int c = idx % TC, row = idx / TC;
+                    const int gg = row % 32, l2 = (row / 32) % L, o = row / (32 * L);
+                    if (l2 < nl && g0 + gg < ngpt && col0 + c < ncol) {
+                        const long long dst = (col0 + c) + ncol * ((lay0 + l2) + nlay * (long long)(g0 + gg));
+                        if (a.out[o]) store_cs(a.out[o] + dst, sb[(size_t)(o * L + l2) * 32 * TCP + gg * TCP + c]);
+                        if (SW && o == 0 && a.out[2]) store_cs(a.out[2] + dst, (Real)0);   // g = 0  :460
+                    }
+                }
+                buf ^= 1;
+            }
+        }
+    }
+
+    // ---- per-column 2-D outputs -------------------------------------------------
+    if (col_ok && g0 + lane < ngpt && a.out2d) {
+        if (SW) {
+            a.out2d[col + ncol * g] = (Real)m.solar[g];                                  // :468-472
+        } else {
+            double a0, a1;
+            const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                 // :408-412
+            const int r = max(it, 1) - 1;
+            a.out2d[col + ncol * g] = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
+        }
+    }
+}
+
+// ============================================================================
+// debug kernels: the indices cell_index / vmr_index / planck_index produce
+// ============================================================================
+template <typename Real>
+__global__ void indices_kernel(const __grid_constant__ DevModel m, const __grid_constant__ GasRef lut, int has_lut,
+                               int ncol_, int nlay_, const Real *plev, const Real *tlay,
+                               int *ip0, double *pw1, int *it0, double *tw1, int *iv0, double *vw1)
+{
+    const long long ncol = ncol_, ncell = ncol * nlay_;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncell) return;
+    const long long col = idx % ncol, lay = idx / ncol;
+    const CellIndex ci = cell_index(m, (double)plev[col + ncol * lay], (double)plev[col + ncol * (lay + 1)],
+                                    (double)tlay[col + ncol * lay]);
+    ip0[idx] = ci.ip0; pw1[idx] = ci.pw1; it0[idx] = ci.it0; tw1[idx] = ci.tw1;
+    int iv = 1; double v1 = 0.0;
+    if (has_lut) iv = vmr_index(lut, load_vmr<Real>(lut, col, lay), v1);
+    iv0[idx] = iv; vw1[idx] = v1;
+}
+
+__global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long long n, const double *T, int *it0, double *w1)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    double a0, a1;
+    const int it = planck_index(m, T[idx], a0, a1);
+    it0[idx] = it; w1[idx] = it > 0 ? a1 : 0.0;
+}
+
+// ============================================================================
+// launchers
+// ============================================================================
+template <typename Real, bool SW, int TC, int L>
+static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
+{
+    constexpr int NOUT = SW ? 2 : 4;
+    const size_t smem = sizeof(Rec<Real>) * TC * 32 + sizeof(Real) * 2 * NOUT * L * 32 * (TC + 1);
+    auto kern = walk_kernel<Real, SW, TC, L>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + 31) / 32));
+    kern<<<grid, TC * 32, smem, s>>>(m, cg, a);
+    return cudaGetLastError();
+}
+
+template <typename Real, bool SW>
+cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
+{
+    return launch_walk_t<Real, SW, 16, 2>(m, cg, a, s);
+}
+
+template <typename Real, bool SW>
+cudaError_t launch_generic(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
+{
+    const long long ncell = (long long)a.ncol * a.nlay;
+    const unsigned blocks = (unsigned)((ncell + 255) / 256);
+    generic_kernel<Real, SW><<<blocks, 256, 0, s>>>(m, cg, a);
+    return cudaGetLastError();
+}
+
+template <typename Real>
+cudaError_t launch_indices(const DevModel &m, const GasRef *lut, int ncol, int nlay, const Real *plev, const Real *tlay,
+                           int *ip0, double *pw1, int *it0, double *tw1, int *iv0, double *vw1, cudaStream_t s)
+{
+    const long long ncell = (long long)ncol * nlay;
+    GasRef dummy{};
+    indices_kernel<Real><<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(m, lut ? *lut : dummy, lut != nullptr, ncol, nlay,
+                                                                        plev, tlay, ip0, pw1, it0, tw1, iv0, vw1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_planck_indices(const DevModel &m, long long n, const double *T, int *it0, double *w1, cudaStream_t s)
+{
+    planck_indices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, n, T, it0, w1);
+    return cudaGetLastError();
+}
+
+#define ECCKD_INST(Real)                                                                                               \
+    template cudaError_t launch_walk<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t); \
+    template cudaError_t launch_walk<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);  \
+    template cudaError_t launch_generic<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t); \
+    template cudaError_t launch_generic<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);  \
+    template cudaError_t launch_indices<Real>(const DevModel &, const GasRef *, int, int, const Real *, const Real *, int *,   \
+                                              double *, int *, double *, int *, double *, cudaStream_t);
+ECCKD_INST(double)
+ECCKD_INST(float)
+
+}  // namespace ecckd

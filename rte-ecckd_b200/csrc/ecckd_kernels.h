@@ -1,0 +1,31 @@
+// ecckd_kernels.h -- host-visible launch interface of ecckd_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ecckd {
+
+struct DevModel;
+struct CallGases;
+struct GasRef;
+
+// Arguments of one gas-optics launch.  All pointers are device memory, Fortran
+// layout (column fastest).  LW: out = {tau, lay_source, lev_source_inc,
+// lev_source_dec}, out2d = sfc_source.  SW: out = {tau, ssa, g, -}, out2d = toa_src.
+// NULL outputs are skipped (reference error paths :414-417, :461-463).
+template <typename Real> struct KernelArgs {
+    int ncol, nlay;
+    const Real *plev, *tlay, *tlev, *tsfc;
+    Real *out[4];
+    Real *out2d;
+};
+
+template <typename Real, bool SW>
+cudaError_t launch_walk(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);
+template <typename Real, bool SW>
+cudaError_t launch_generic(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);
+template <typename Real>
+cudaError_t launch_indices(const DevModel &, const GasRef *lut, int ncol, int nlay, const Real *plev, const Real *tlay,
+                           int *ip0, double *pw1, int *it0, double *tw1, int *iv0, double *vw1, cudaStream_t);
+cudaError_t launch_planck_indices(const DevModel &, long long n, const double *T, int *it0, double *w1, cudaStream_t);
+
+}  // namespace ecckd
