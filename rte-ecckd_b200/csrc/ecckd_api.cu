@@ -127,8 +127,8 @@ int resolve_gases(const ecckd_model *M, int ngas, const char *const *names, cons
         g.ref = M->ref[i]; g.nv = M->nv[i];
         g.mf0 = M->mf0[i]; g.log_mf0 = M->log_mf0[i]; g.dlog_mf = M->dlog_mf[i];
         g.v_clamp = (double)M->nv[i] - 1.001;                                          // :160
-        if (g.code == kLut) { if (nlut++ == 0) cg.lut = cg.n; }
-        else if (cg.nbil < kMaxBil) cg.bil[cg.nbil++] = cg.n;
+        if (g.code == kLut) { if (nlut++ == 0) { cg.lut = cg.n; cg.lut_off = (int)g.table_off; } }
+        else if (cg.nbil < kMaxBil) { cg.bil_off[cg.nbil] = (int)g.table_off; cg.bil[cg.nbil++] = cg.n; }
         else cg.nbil = kMaxBil + 1;
         ++cg.n;
         if (M->composite_only[i]) first_calc = false;                                  // :371-373
@@ -412,6 +412,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         if (g.composite_only) { composite_off = (long long)k64.size(); composite_src = g.coefficient; }
         k64.insert(k64.end(), g.coefficient, g.coefficient + n);
     }
+    if (k64.size() >= (size_t)1 << 30) { set_err(err, "ecckd_model_create: tables too large"); return ECCKD_ERR_ARG; }
     std::vector<float> k32(k64.size());
     for (size_t q = 0; q < k64.size(); ++q) {
         k32[q] = (float)k64[q];

@@ -57,6 +57,8 @@ struct CallGases {
     int nbil;               // number of code 0/1/3 gases
     int lut;                // index in g[] of the (single) LUT gas, or -1
     int bil[kMaxBil];       // indices in g[] of the bilinear gases, caller order
+    int bil_off[kMaxBil];   // their table offsets (elements; all tables together are < 2^31 elements)
+    int lut_off;            // table offset of the LUT gas
     GasRef g[kMaxGases];
 };
 

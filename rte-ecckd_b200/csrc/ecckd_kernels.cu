@@ -130,40 +130,70 @@ generic_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallG
 // column-walking kernel
 // ============================================================================
 // Per-(warp, layer) record produced by the lane-distributed index phase and read
-// back as warp-wide broadcasts.
+// back as warp-wide broadcasts (every lane reads the same address: one wavefront
+// per 16-byte vector load).  Field groups are 16-byte aligned for both real kinds.
 template <typename Real> struct alignas(16) Rec {
     Real c[4];          // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
     Real w[kMaxBil];    // weight of each bilinear gas
-    Real wl, vw1;       // LUT gas: weight, vmr_weight1
     Real pa[4];         // LW: lay (a0,a1)/pi, lower level (a0,a1)/pi.  SW: pa[0] = moles_per_layer
-    int ip, it, iv, prow;   // 0-based corner indices; prow = lay_row | lev_row << 16
+    Real wl, vw1;       // LUT gas: weight, vmr_weight1
+    alignas(16) int ip; // 0-based corner indices
+    int it, iv;
+    int prow;           // Planck rows: lay_row | lev_row << 16
 };
+static_assert(sizeof(Rec<double>) == 160 && sizeof(Rec<float>) == 96, "record layout");
 
-template <typename Real, bool SW, int TC, int L>
-__global__ void __launch_bounds__(TC * 32, 1)
+template <typename Real> struct Pair { Real x, y; };
+template <typename Real> __device__ __forceinline__ void lds4(const Real *p, Real &a, Real &b, Real &c, Real &d);
+template <> __device__ __forceinline__ void lds4<double>(const double *p, double &a, double &b, double &c, double &d)
+{
+    const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
+    a = u.x; b = u.y; c = v.x; d = v.y;
+}
+template <> __device__ __forceinline__ void lds4<float>(const float *p, float &a, float &b, float &c, float &d)
+{
+    const float4 u = *reinterpret_cast<const float4 *>(p);
+    a = u.x; b = u.y; c = u.z; d = u.w;
+}
+template <typename Real> __device__ __forceinline__ void lds2(const Real *p, Real &a, Real &b);
+template <> __device__ __forceinline__ void lds2<double>(const double *p, double &a, double &b)
+{
+    const double2 u = *reinterpret_cast<const double2 *>(p);
+    a = u.x; b = u.y;
+}
+template <> __device__ __forceinline__ void lds2<float>(const float *p, float &a, float &b)
+{
+    const float2 u = *reinterpret_cast<const float2 *>(p);
+    a = u.x; b = u.y;
+}
+
+template <typename Real, bool SW, int TC, int L, int MINB>
+__global__ void __launch_bounds__(TC * 32, MINB)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a)
 {
     constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled at write-out
     constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
+    constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
+    constexpr int NTHR = TC * 32;
+    static_assert(NTHR / TC == 32, "write-out maps one thread row per g-point");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Rec<Real> *recs = reinterpret_cast<Rec<Real> *>(smem_raw);
     Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(Rec<Real>) * TC * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long ncol = a.ncol, nlay = a.nlay;
+    const int ncol = a.ncol, nlay = a.nlay;
     const long long col0 = (long long)blockIdx.x * TC;
     const long long col = col0 + warp;
     const bool col_ok = col < ncol;
-    const int ngpt = m.ngpt, np = m.np;
+    const int ngpt = m.ngpt;
     const int g0 = blockIdx.y * 32;
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
     const Real *ktab = TableOf<Real>::k(m) + g;
     const Real *ptab = TableOf<Real>::planck(m) + g;
-    const long long s_t = (long long)ngpt * np, s_v = s_t * m.nt;
+    const int s_t = ngpt * m.np, s_v = s_t * m.nt;   // table strides in elements (tables are far below 2^31 elements)
     const int nbil = cg.nbil;
     const bool has_lut = cg.lut >= 0;
-    const long long lut_off = has_lut ? cg.g[cg.lut].table_off : 0;
 
     Real kb[kMaxBil][4];
     Real kh[8];
@@ -182,16 +212,24 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         lev_prev = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
     }
 
+    // per-thread constants of the staging tile and of the cooperative write-out
+    const Rec<Real> *myrecs = recs + warp * 32;
+    Real *st_mine = stage + lane * TCP + warp;             // + (buf*NOUT*L + o*L + ls) * ROWS
+    const int wo_c = threadIdx.x % TC, wo_g = threadIdx.x / TC;
+    const bool wo_ok = (g0 + wo_g < ngpt) && (col0 + wo_c < ncol);
+    const long long wo_base = (col0 + wo_c) + (long long)ncol * nlay * (g0 + wo_g);
+    const Real *wo_st = stage + wo_g * TCP + wo_c;
+
     int buf = 0;
-    for (long long j0 = 0; j0 < nlay; j0 += 32) {
+    for (int j0 = 0; j0 < nlay; j0 += 32) {
         // ---- phase A: lane l computes the record of layer j0 + l ----------------
         __syncwarp();
         {
-            const long long j = j0 + lane;
+            const int j = j0 + lane;
             if (col_ok && j < nlay) {
                 Rec<Real> r;
-                const double pu = (double)a.plev[col + ncol * j], pl = (double)a.plev[col + ncol * (j + 1)];
-                const double tl = (double)a.tlay[col + ncol * j];
+                const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
+                const double tl = (double)a.tlay[col + (long long)ncol * j];
                 const CellIndex ci = cell_index(m, pu, pl, tl);
                 const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
                 r.c[0] = (Real)(tw0 * pw0); r.c[1] = (Real)(tw0 * ci.pw1);
@@ -225,7 +263,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     int rows = max(it, 1) - 1;
                     r.pa[0] = (Real)__ddiv_rn(a0, m.pi); r.pa[1] = (Real)__ddiv_rn(a1, m.pi);
                     if (a.tlev) {
-                        it = planck_index(m, (double)a.tlev[col + ncol * (j + 1)], a0, a1);
+                        it = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
                         rows |= (max(it, 1) - 1) << 16;
                         r.pa[2] = (Real)__ddiv_rn(a0, m.pi); r.pa[3] = (Real)__ddiv_rn(a1, m.pi);
                     }
@@ -237,20 +275,23 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         __syncwarp();
 
         // ---- phase B: walk the (up to) 32 layers of this chunk ------------------
-        const int nl_chunk = (int)min((long long)32, nlay - j0);
+        const int nl_chunk = min(32, nlay - j0);
         for (int l = 0; l < nl_chunk; ++l) {
-            const long long j = j0 + l;
-            const int ls = (int)(j % L);
+            const int j = j0 + l;
+            const int ls = j % L;
             if (col_ok) {
-                const Rec<Real> &r = recs[warp * 32 + l];
-                const int ip = r.ip, it = r.it;
+                const Rec<Real> *rp = myrecs + l;
+                const int4 ix = *reinterpret_cast<const int4 *>(&rp->ip);
+                Real c0, c1, c2, c3;
+                lds4<Real>(rp->c, c0, c1, c2, c3);
+                const int ip = ix.x, it = ix.y;
+                const int coff = ngpt * ip + s_t * it;
                 if (ip != cur_ip || it != cur_it) {
                     const bool shift = (ip == cur_ip + 1) && (it == cur_it);
-                    const Real *corner = ktab + (long long)ngpt * ip + s_t * it;
 #pragma unroll
                     for (int b = 0; b < kMaxBil; ++b) {
                         if (b < nbil) {
-                            const Real *k = corner + cg.g[cg.bil[b]].table_off;
+                            const Real *k = ktab + (cg.bil_off[b] + coff);
                             if (shift) { kb[b][0] = kb[b][1]; kb[b][2] = kb[b][3]; }
                             else { kb[b][0] = k[0]; kb[b][2] = k[s_t]; }
                             kb[b][1] = k[ngpt]; kb[b][3] = k[s_t + ngpt];
@@ -260,65 +301,73 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
                 Real tau = 0;
                 if (has_lut) {
-                    const int iv = r.iv;
+                    const int iv = ix.z;
                     if (ip != cur_hp || it != cur_ht || iv != cur_hv) {
-                        const Real *k = ktab + lut_off + (long long)ngpt * ip + s_t * it + s_v * iv;
+                        const Real *k = ktab + (cg.lut_off + coff + s_v * iv);
                         kh[0] = k[0]; kh[1] = k[ngpt]; kh[2] = k[s_t]; kh[3] = k[s_t + ngpt];
                         k += s_v;
                         kh[4] = k[0]; kh[5] = k[ngpt]; kh[6] = k[s_t]; kh[7] = k[s_t + ngpt];
                         cur_hp = ip; cur_ht = it; cur_hv = iv;
                     }
-                    const Real wl = r.wl;
+                    Real wl, v1;
+                    lds2<Real>(&rp->wl, wl, v1);
                     if (!(wl < (Real)0)) {
-                        const Real b0 = r.c[0] * kh[0] + r.c[1] * kh[1] + r.c[2] * kh[2] + r.c[3] * kh[3];
-                        const Real b1 = r.c[0] * kh[4] + r.c[1] * kh[5] + r.c[2] * kh[6] + r.c[3] * kh[7];
-                        const Real v1 = r.vw1;
-                        tau = wl * (((Real)1 - v1) * b0 + v1 * b1);
+                        const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
+                        const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
+                        tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < kMaxBil; ++b) {
+                for (int b = 0; b < kMaxBil; b += 2) {
                     if (b < nbil) {
-                        const Real wv = r.w[b];
+                        Real w0, w1;
+                        lds2<Real>(&rp->w[b], w0, w1);
                         // tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the
-                        // per-g clamp (:233-238) is a warp-uniform skip
-                        if (!(wv < (Real)0)) {
-                            const Real bil = r.c[0] * kb[b][0] + r.c[1] * kb[b][1] + r.c[2] * kb[b][2] + r.c[3] * kb[b][3];
-                            tau += wv * bil;
-                        }
+                        // per-g clamp (:233-238) is a warp-uniform skip of the whole gas
+                        if (!(w0 < (Real)0))
+                            tau += w0 * (c0 * kb[b][0] + c1 * kb[b][1] + c2 * kb[b][2] + c3 * kb[b][3]);
+                        if (b + 1 < nbil && !(w1 < (Real)0))
+                            tau += w1 * (c0 * kb[b + 1][0] + c1 * kb[b + 1][1] + c2 * kb[b + 1][2] + c3 * kb[b + 1][3]);
                     }
                 }
-                Real *st = stage + (size_t)buf * NOUT * L * 32 * TCP + (size_t)ls * 32 * TCP + lane * TCP + warp;
+                Real *st = st_mine + (buf * NOUT * L + ls) * ROWS;
                 if (SW) {
-                    const Real ray = r.pa[0] * sigma;               // :313-316
+                    const Real ray = rp->pa[0] * sigma;             // :313-316
                     tau += ray;                                     // :456
                     st[0] = tau;
-                    st[(size_t)L * 32 * TCP] = ray / tau;           // :459
+                    st[L * ROWS] = ray / tau;                       // :459
                 } else {
-                    const int rl = r.prow & 0xffff, rv = r.prow >> 16;
-                    const Real lay_src = r.pa[0] * ptab[rl * ngpt] + r.pa[1] * ptab[(rl + 1) * ngpt];
-                    const Real lev_next = r.pa[2] * ptab[rv * ngpt] + r.pa[3] * ptab[(rv + 1) * ngpt];
+                    Real p0, p1, p2, p3;
+                    lds4<Real>(rp->pa, p0, p1, p2, p3);
+                    const int rl = (ix.w & 0xffff) * ngpt, rv = (ix.w >> 16) * ngpt;
+                    const Real lay_src = p0 * ptab[rl] + p1 * ptab[rl + ngpt];
+                    const Real lev_next = p2 * ptab[rv] + p3 * ptab[rv + ngpt];
                     st[0] = tau;
-                    st[(size_t)1 * L * 32 * TCP] = lay_src;
-                    st[(size_t)2 * L * 32 * TCP] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
-                    st[(size_t)3 * L * 32 * TCP] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
+                    st[1 * L * ROWS] = lay_src;
+                    st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
+                    st[3 * L * ROWS] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
                     lev_prev = lev_next;
                 }
             }
             if (ls == L - 1 || j == nlay - 1) {
                 __syncthreads();
-                const int nl = ls + 1;
-                const long long lay0 = j - ls;
-                const Real *sb = stage + (size_t)buf * NOUT * L * 32 * TCP;
+                if (wo_ok) {
+                    const int nl = ls + 1;
+                    const long long off0 = wo_base + (long long)ncol * (j - ls);
+                    const Real *sb = wo_st + buf * NOUT * L * ROWS;
 #pragma unroll
-                for (int it2 = 0; it2 < NOUT * L; ++it2) {
-                    const int idx = it2 * (TC * 32) + threadIdx.x;
-                    const int c = idx % TC, row = idx / TC;
-                    const int gg = row % 32, l2 = (row / 32) % L, o = row / (32 * L);
-                    if (l2 < nl && g0 + gg < ngpt && col0 + c < ncol) {
-                        const long long dst = (col0 + c) + ncol * ((lay0 + l2) + nlay * (long long)(g0 + gg));
-                        if (a.out[o]) store_cs(a.out[o] + dst, sb[(size_t)(o * L + l2) * 32 * TCP + gg * TCP + c]);
-                        if (SW && o == 0 && a.out[2]) store_cs(a.out[2] + dst, (Real)0);   // g = 0  :460
+                    for (int o = 0; o < NOUT; ++o) {
+                        Real *dst = a.out[o];
+                        if (dst) {
+#pragma unroll
+                            for (int l2 = 0; l2 < L; ++l2)
+                                if (l2 < nl) store_cs(dst + off0 + (long long)ncol * l2, sb[(o * L + l2) * ROWS]);
+                        }
+                    }
+                    if (SW && a.out[2]) {
+#pragma unroll
+                        for (int l2 = 0; l2 < L; ++l2)
+                            if (l2 < nl) store_cs(a.out[2] + off0 + (long long)ncol * l2, (Real)0);   // g = 0  :460
                     }
                 }
                 buf ^= 1;
@@ -329,12 +378,12 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // ---- per-column 2-D outputs -------------------------------------------------
     if (col_ok && g0 + lane < ngpt && a.out2d) {
         if (SW) {
-            a.out2d[col + ncol * g] = (Real)m.solar[g];                                  // :468-472
+            a.out2d[col + (long long)ncol * g] = (Real)m.solar[g];                                  // :468-472
         } else {
             double a0, a1;
-            const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                 // :408-412
+            const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                            // :408-412
             const int r = max(it, 1) - 1;
-            a.out2d[col + ncol * g] = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
+            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
         }
     }
 }
@@ -371,12 +420,12 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // ============================================================================
 // launchers
 // ============================================================================
-template <typename Real, bool SW, int TC, int L>
+template <typename Real, bool SW, int TC, int L, int MINB>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 4;
     const size_t smem = sizeof(Rec<Real>) * TC * 32 + sizeof(Real) * 2 * NOUT * L * 32 * (TC + 1);
-    auto kern = walk_kernel<Real, SW, TC, L>;
+    auto kern = walk_kernel<Real, SW, TC, L, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + 31) / 32));
@@ -387,7 +436,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
 template <typename Real, bool SW>
 cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
 {
-    return launch_walk_t<Real, SW, 16, 2>(m, cg, a, s);
+    return launch_walk_t<Real, SW, 16, 2, 1>(m, cg, a, s);
 }
 
 template <typename Real, bool SW>
