@@ -68,6 +68,9 @@ struct ecckd_model {
     std::vector<int> composite_only, code, nv;
     std::vector<double> ref, mf0, log_mf0, dlog_mf;
     std::vector<long long> table_off;
+    std::vector<int> slot;      // walk-table slot of each bilinear gas (-1: LUT gas)
+    bool walk_model = false;    // walk tables were built (see ecckd_model_create)
+    int nslot_ = 0, nv_lut_ = 0;
     std::vector<double> log_pressure, temperature, band_lims;
     std::vector<int32_t> band2gpt;
     double total_solar = 0.0;
@@ -109,7 +112,7 @@ int resolve_gases(const ecckd_model *M, int ngas, const char *const *names, cons
     std::memset(&cg, 0, sizeof(cg));
     cg.lut = -1;
     int nlut = 0;
-    bool first_calc = true;
+    bool first_calc = true, many = false;
     if (ngas < 0 || (ngas > 0 && (!names || !vmr))) { set_err(err, "ecckd: bad gas list"); return ECCKD_ERR_ARG; }
     for (int j = 0; j < ngas; ++j) {                                                   // :348
         const std::string want = trim_name(names[j], 4096);
@@ -127,14 +130,25 @@ int resolve_gases(const ecckd_model *M, int ngas, const char *const *names, cons
         g.ref = M->ref[i]; g.nv = M->nv[i];
         g.mf0 = M->mf0[i]; g.log_mf0 = M->log_mf0[i]; g.dlog_mf = M->dlog_mf[i];
         g.v_clamp = (double)M->nv[i] - 1.001;                                          // :160
-        if (g.code == kLut) { if (nlut++ == 0) { cg.lut = cg.n; cg.lut_off = (int)g.table_off; } }
-        else if (cg.nbil < kMaxBil) { cg.bil_off[cg.nbil] = (int)g.table_off; cg.bil[cg.nbil++] = cg.n; }
-        else cg.nbil = kMaxBil + 1;
+        if (g.code == kLut) { if (nlut++ == 0) cg.lut = cg.n; }
+        else {
+            ++cg.nbil;
+            if (M->walk_model) {
+                // call-constant weight factor (code 0, or a scalar concentration) -> mixed table; else a register slot
+                const bool constant = g.code == kNone || (g.col_stride == 0 && g.lay_stride == 0);
+                if (constant) {
+                    if (cg.nmix < kMaxBil) { cg.mix_gas[cg.nmix] = cg.n; cg.mix_off[cg.nmix] = M->slot[i] * kSlab; ++cg.nmix; }
+                    else many = true;
+                } else {
+                    if (cg.nvar < kMaxBil - 1) { cg.var_gas[cg.nvar] = cg.n; cg.var_off[cg.nvar] = M->slot[i] * kSlab; ++cg.nvar; }
+                    else many = true;
+                }
+            }
+        }
         ++cg.n;
         if (M->composite_only[i]) first_calc = false;                                  // :371-373
     }
-    walk_ok = M->tables_nonneg && nlut <= 1 && cg.nbil <= kMaxBil;
-    if (cg.nbil > kMaxBil) cg.nbil = kMaxBil;
+    walk_ok = M->walk_model && nlut <= 1 && !many;
     return ECCKD_OK;
 }
 
@@ -182,9 +196,18 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
         } else if (kernel == ECCKD_KERNEL_GENERIC) use_walk = false;
         else { set_err(err, "ecckd: unknown kernel selector"); return ECCKD_ERR_ARG; }
         cudaError_t e;
-        if (use_walk) e = sw ? launch_walk<Real, true>(d.dm, cg, a, stream) : launch_walk<Real, false>(d.dm, cg, a, stream);
-        else e = sw ? launch_generic<Real, true>(d.dm, cg, a, stream) : launch_generic<Real, false>(d.dm, cg, a, stream);
-        CUDA_TRY(e);
+        if (use_walk) {
+            // stream-ordered scratch for the per-call mixed table: safe for concurrent calls on other streams
+            void *scratch = nullptr;
+            CUDA_TRY(cudaMallocAsync(&scratch, walk_scratch_bytes(d.dm, cg, sizeof(Real)), stream));
+            e = sw ? launch_walk<Real, true>(d.dm, cg, a, scratch, stream) : launch_walk<Real, false>(d.dm, cg, a, scratch, stream);
+            cudaError_t e2 = cudaFreeAsync(scratch, stream);
+            CUDA_TRY(e);
+            CUDA_TRY(e2);
+        } else {
+            e = sw ? launch_generic<Real, true>(d.dm, cg, a, stream) : launch_generic<Real, false>(d.dm, cg, a, stream);
+            CUDA_TRY(e);
+        }
     }
     if (lev_missing) { set_err(err, "tlev is required for ecckd"); return ECCKD_ERR_REFERENCE; }              // :414-417
     if (not_2str) { set_err(err, "shortwave must use ty_optical_props_2str"); return ECCKD_ERR_REFERENCE; }    // :461-463
@@ -426,6 +449,56 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         p32.resize(p64.size());
         for (size_t q = 0; q < p64.size(); ++q) { p32[q] = (float)p64[q]; if ((double)p32[q] != p64[q]) M->fp32_exact = false; }
     }
+    // ---- walk tables: padded, g-grouped copies with compile-time corner offsets ----
+    // Qualifies when extents fit the padding, at most one look-up-table gas, at most
+    // kMaxBil distinct bilinear tables, and no negative coefficient (so that the
+    // per-g clamp :233-238 reduces to a per-gas sign test of the weight).
+    std::vector<double> wbil64, wlut64, wpl64;
+    {
+        int nlut = 0, lut_gas = -1, nslot = 0;
+        std::vector<long long> slot_off;
+        M->slot.assign(t->num_gases, -1);
+        for (int i = 0; i < t->num_gases; ++i) {
+            if (M->code[i] == ECCKD_CODE_LOOK_UP_TABLE) { ++nlut; lut_gas = i; continue; }
+            int sidx = -1;
+            for (int q = 0; q < nslot; ++q) if (slot_off[q] == M->table_off[i]) sidx = q;
+            if (sidx < 0) { sidx = nslot++; slot_off.push_back(M->table_off[i]); }
+            M->slot[i] = sidx;
+        }
+        M->walk_model = M->tables_nonneg && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP;
+        if (M->walk_model) {
+            const int ngroups = (t->ngpt + kGP - 1) / kGP, ng = t->ngpt, np = t->npress, nt = t->ntemp;
+            const int nvl = lut_gas >= 0 ? M->nv[lut_gas] : 0;
+            wbil64.assign((size_t)ngroups * std::max(nslot, 1) * kSlab, 0.0);
+            wlut64.assign((size_t)ngroups * std::max(nvl, 1) * kSlab, 0.0);
+            for (int grp = 0; grp < ngroups; ++grp)
+                for (int ln = 0; ln < kGP; ++ln) {
+                    const int g = grp * kGP + ln;
+                    if (g >= ng) continue;
+                    for (int ip = 0; ip < np; ++ip)
+                        for (int it = 0; it < nt; ++it) {
+                            const size_t cell = ((size_t)ip * kNTP + it) * kGP + ln;
+                            const size_t src = (size_t)g + (size_t)ng * (ip + (size_t)np * it);
+                            for (int q = 0; q < nslot; ++q)
+                                wbil64[((size_t)grp * nslot + q) * kSlab + cell] = k64[slot_off[q] + src];
+                            for (int iv = 0; iv < nvl; ++iv)
+                                wlut64[((size_t)grp * nvl + iv) * kSlab + cell] =
+                                    k64[M->table_off[lut_gas] + src + (size_t)ng * np * nt * iv];
+                        }
+                }
+            if (!t->shortwave) {
+                wpl64.assign((size_t)ngroups * t->nplanck * kGP, 0.0);
+                for (int grp = 0; grp < ngroups; ++grp)
+                    for (int r = 0; r < t->nplanck; ++r)
+                        for (int ln = 0; ln < kGP; ++ln)
+                            if (grp * kGP + ln < ng)
+                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln];
+            }
+        }
+        M->nslot_ = nslot; M->nv_lut_ = lut_gas >= 0 ? M->nv[lut_gas] : 0;
+    }
+    auto narrow = [](const std::vector<double> &v) { std::vector<float> f(v.size()); for (size_t q = 0; q < v.size(); ++q) f[q] = (float)v[q]; return f; };
+    const std::vector<float> wbil32 = narrow(wbil64), wlut32 = narrow(wlut64), wpl32 = narrow(wpl64);
     std::vector<double> tbase(t->temperature, t->temperature + t->npress);               // temperature(:,1)
     std::vector<double> ray, sol;
     if (t->shortwave) {
@@ -461,6 +534,15 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         if ((rc = upload(d2, p32, &d2.dm.planck32, err))) return rc;
         if ((rc = upload(d2, ray, &d2.dm.rayleigh, err))) return rc;
         if ((rc = upload(d2, sol, &d2.dm.solar, err))) return rc;
+        d2.dm.nslot = M->nslot_; d2.dm.nv_lut = M->nv_lut_;
+        if ((rc = upload(d2, wbil64, &d2.dm.wbil64, err))) return rc;
+        if ((rc = upload(d2, wlut64, &d2.dm.wlut64, err))) return rc;
+        if ((rc = upload(d2, wpl64, &d2.dm.wpl64, err))) return rc;
+        if (M->fp32_exact) {
+            if ((rc = upload(d2, wbil32, &d2.dm.wbil32, err))) return rc;
+            if ((rc = upload(d2, wlut32, &d2.dm.wlut32, err))) return rc;
+            if ((rc = upload(d2, wpl32, &d2.dm.wpl32, err))) return rc;
+        }
     }
     *out = M.release();
     return ECCKD_OK;

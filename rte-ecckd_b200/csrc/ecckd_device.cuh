@@ -13,7 +13,15 @@
 namespace ecckd {
 
 constexpr int kMaxGases = 16;  // gas_optics_ecckd.f90:24
-constexpr int kMaxBil = 8;     // bilinear (code 0/1/3) gases the walking kernel keeps in registers
+constexpr int kMaxBil = 8;     // bilinear (code 0/1/3) table slots the walking kernel keeps in registers
+
+// Padded "walk" table geometry: every dimension that enters a corner offset is a
+// compile-time constant, so the 4 (8) corner loads of every slot are immediate
+// offsets from ONE base pointer per (ip0,it0[,iv0]) change.
+constexpr int kGP = 32;                    // g-points per group = lanes per warp
+constexpr int kNTP = 8;                    // padded temperature extent   (ntemp  <= 8)
+constexpr int kNPP = 64;                   // padded pressure extent      (npress <= 64)
+constexpr int kSlab = kNPP * kNTP * kGP;   // elements of one (slot | mole-fraction) slab
 
 enum Code : int { kNone = 0, kLinear = 1, kLut = 2, kRelLinear = 3 };  // :54-57
 
@@ -35,6 +43,13 @@ struct DevModel {
     const double *planck64;
     const double *rayleigh;  // (ngpt)
     const double *solar;     // (ngpt)
+    // walk tables (NULL when the model does not qualify): per g-group of 32,
+    //   wbil [group][slot][ip][it][lane]   slot = distinct bilinear table, model order, composite once
+    //   wlut [group][iv][ip][it][lane]     the single look-up-table gas
+    //   wpl  [group][itp][lane]            planck_function
+    int nslot, nv_lut;
+    const double *wbil64, *wlut64, *wpl64;
+    const float *wbil32, *wlut32, *wpl32;
 };
 
 // One active gas of this call, already resolved against the model on the host
@@ -56,9 +71,16 @@ struct CallGases {
     int n;
     int nbil;               // number of code 0/1/3 gases
     int lut;                // index in g[] of the (single) LUT gas, or -1
-    int bil[kMaxBil];       // indices in g[] of the bilinear gases, caller order
-    int bil_off[kMaxBil];   // their table offsets (elements; all tables together are < 2^31 elements)
-    int lut_off;            // table offset of the LUT gas
+    // ---- plan of the walking kernel (host-filled when the call qualifies) ----
+    // Bilinear interpolation is linear in the table, so every gas whose weight
+    // factor is constant over the call (scalar vmr, or code 0) is pre-mixed into
+    // ONE table per call:  sum_g (sw*f_g)*bil(K_g) == sw*bil(sum_g f_g*K_g).
+    int nvar;               // bilinear gases whose vmr varies over the call: register slots 1..nvar
+    int var_gas[kMaxBil];   //   index in g[]
+    int var_off[kMaxBil];   //   element offset of their slab inside one g-group of wbil
+    int nmix;               // bilinear gases with a call-constant factor: mixed into slot 0
+    int mix_gas[kMaxBil];
+    int mix_off[kMaxBil];
     GasRef g[kMaxGases];
 };
 
@@ -66,10 +88,16 @@ template <typename Real> struct TableOf;
 template <> struct TableOf<double> {
     __device__ static const double *k(const DevModel &m) { return m.k64; }
     __device__ static const double *planck(const DevModel &m) { return m.planck64; }
+    __device__ static const double *wbil(const DevModel &m) { return m.wbil64; }
+    __device__ static const double *wlut(const DevModel &m) { return m.wlut64; }
+    __device__ static const double *wpl(const DevModel &m) { return m.wpl64; }
 };
 template <> struct TableOf<float> {
     __device__ static const float *k(const DevModel &m) { return m.k32; }
     __device__ static const float *planck(const DevModel &m) { return m.planck32; }
+    __device__ static const float *wbil(const DevModel &m) { return m.wbil32; }
+    __device__ static const float *wlut(const DevModel &m) { return m.wlut32; }
+    __device__ static const float *wpl(const DevModel &m) { return m.wpl32; }
 };
 
 // ---- per-cell interpolation state (pressure, temperature) -------------------

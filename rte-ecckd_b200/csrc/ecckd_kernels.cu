@@ -129,21 +129,48 @@ generic_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallG
 // ============================================================================
 // column-walking kernel
 // ============================================================================
+// ---- per-call table mixing ----------------------------------------------------
+// out[sign][group][ip][it][lane]: sign 0 = sum of f_g*K_g over gases with f_g not < 0,
+// sign 1 = the same over gases with f_g < 0 (only reachable by cells whose
+// simple_weight is negative, i.e. upside-down layers -- kept so that the
+// reference's sign logic :143-149,233-238 is reproduced for them too).
+// f_g: 1 (code 0, :216), vmr (code 1, :148), vmr - reference (code 3, :146).
+template <typename Real>
+__global__ void __launch_bounds__(256)
+mix_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, Real *out)
+{
+    const int ngroups = (m.ngpt + kGP - 1) / kGP;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ngroups * kSlab) return;
+    const int grp = e / kSlab, cell = e % kSlab;
+    const double *src = m.wbil64 + (size_t)grp * m.nslot * kSlab + cell;
+    double plus = 0.0, minus = 0.0;
+    for (int q = 0; q < cg.nmix; ++q) {
+        const GasRef &gr = cg.g[cg.mix_gas[q]];
+        const double vmr = gr.code == kNone ? 0.0 : load_vmr<Real>(gr, 0, 0);
+        const double f = gr.code == kNone ? 1.0 : (gr.code == kRelLinear ? __dsub_rn(vmr, gr.ref) : vmr);
+        const double kv = src[cg.mix_off[q]];
+        if (f < 0.0) minus += f * kv; else plus += f * kv;
+    }
+    out[e] = (Real)plus;
+    out[(size_t)ngroups * kSlab + e] = (Real)minus;
+}
+
+// ---- records ------------------------------------------------------------------
 // Per-(warp, layer) record produced by the lane-distributed index phase and read
 // back as warp-wide broadcasts (every lane reads the same address: one wavefront
 // per 16-byte vector load).  Field groups are 16-byte aligned for both real kinds.
-template <typename Real> struct alignas(16) Rec {
+template <typename Real, int NB> struct alignas(16) Rec {
     Real c[4];          // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
-    Real w[kMaxBil];    // weight of each bilinear gas
     Real pa[4];         // LW: lay (a0,a1)/pi, lower level (a0,a1)/pi.  SW: pa[0] = moles_per_layer
+    Real w[NB];         // w[0] = simple_weight (mixed table); w[s] = weight of varying gas s-1
     Real wl, vw1;       // LUT gas: weight, vmr_weight1
-    alignas(16) int ip; // 0-based corner indices
-    int it, iv;
+    alignas(16) int pk; // bilinear corner key  ip*kNTP + it          (0-based ip, it)
+    int hk;             // LUT corner key       (iv*kNPP + ip)*kNTP + it
     int prow;           // Planck rows: lay_row | lev_row << 16
+    int mask;           // bit s: slot s contributes; bit 8: LUT gas; bit 9: negative-weight mix (slow path)
 };
-static_assert(sizeof(Rec<double>) == 160 && sizeof(Rec<float>) == 96, "record layout");
 
-template <typename Real> struct Pair { Real x, y; };
 template <typename Real> __device__ __forceinline__ void lds4(const Real *p, Real &a, Real &b, Real &c, Real &d);
 template <> __device__ __forceinline__ void lds4<double>(const double *p, double &a, double &b, double &c, double &d)
 {
@@ -167,19 +194,23 @@ template <> __device__ __forceinline__ void lds2<float>(const float *p, float &a
     a = u.x; b = u.y;
 }
 
-template <typename Real, bool SW, int TC, int L, int MINB>
+// corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
+constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
+
+// NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
+// 1..NB-1 the gases whose concentration varies over the call.
+template <typename Real, bool SW, int NB, int TC, int L, int MINB>
 __global__ void __launch_bounds__(TC * 32, MINB)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
-            const __grid_constant__ KernelArgs<Real> a)
+            const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab)
 {
     constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled at write-out
     constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
-    constexpr int NTHR = TC * 32;
-    static_assert(NTHR / TC == 32, "write-out maps one thread row per g-point");
+    using RecT = Rec<Real, NB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Rec<Real> *recs = reinterpret_cast<Rec<Real> *>(smem_raw);
-    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(Rec<Real>) * TC * 32);
+    RecT *recs = reinterpret_cast<RecT *>(smem_raw);
+    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * TC * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
@@ -187,33 +218,35 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const long long col = col0 + warp;
     const bool col_ok = col < ncol;
     const int ngpt = m.ngpt;
-    const int g0 = blockIdx.y * 32;
+    const int grp = blockIdx.y, g0 = grp * kGP;
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
-    const Real *ktab = TableOf<Real>::k(m) + g;
-    const Real *ptab = TableOf<Real>::planck(m) + g;
-    const int s_t = ngpt * m.np, s_v = s_t * m.nt;   // table strides in elements (tables are far below 2^31 elements)
-    const int nbil = cg.nbil;
-    const bool has_lut = cg.lut >= 0;
+    const int nvar = cg.nvar;
+    const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
+    const int ngroups = gridDim.y;
+    const Real *wbil = TableOf<Real>::wbil(m) + (size_t)grp * m.nslot * kSlab + lane;
+    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
+    const Real *wpl = TableOf<Real>::wpl(m) + (size_t)grp * m.nplanck * kGP + lane;
+    const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
 
-    Real kb[kMaxBil][4];
+    Real kb[NB][4];
     Real kh[8];
 #pragma unroll
-    for (int b = 0; b < kMaxBil; ++b) kb[b][0] = kb[b][1] = kb[b][2] = kb[b][3] = 0;
+    for (int s = 0; s < NB; ++s) kb[s][0] = kb[s][1] = kb[s][2] = kb[s][3] = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) kh[i] = 0;
-    int cur_ip = -2, cur_it = -2, cur_hp = -2, cur_ht = -2, cur_hv = -2;
+    int cur_pk = -0x10000, cur_hk = -0x10000;
 
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
     Real lev_prev = 0;   // Planck source at the upper level of the current layer
     if (!SW && col_ok && a.tlev) {
         double a0, a1;
         const int it = planck_index(m, (double)a.tlev[col], a0, a1);
-        const int r = max(it, 1) - 1;
-        lev_prev = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
+        const Real *p = wpl + (max(it, 1) - 1) * kGP;
+        lev_prev = (Real)__ddiv_rn(a0, m.pi) * p[0] + (Real)__ddiv_rn(a1, m.pi) * p[kGP];
     }
 
     // per-thread constants of the staging tile and of the cooperative write-out
-    const Rec<Real> *myrecs = recs + warp * 32;
+    const RecT *myrecs = recs + warp * 32;
     Real *st_mine = stage + lane * TCP + warp;             // + (buf*NOUT*L + o*L + ls) * ROWS
     const int wo_c = threadIdx.x % TC, wo_g = threadIdx.x / TC;
     const bool wo_ok = (g0 + wo_g < ngpt) && (col0 + wo_c < ncol);
@@ -222,113 +255,123 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     int buf = 0;
     for (int j0 = 0; j0 < nlay; j0 += 32) {
+        const int len = min(32, nlay - j0);
         // ---- phase A: lane l computes the record of layer j0 + l ----------------
         __syncwarp();
-        {
+        if (col_ok && lane < len) {
             const int j = j0 + lane;
-            if (col_ok && j < nlay) {
-                Rec<Real> r;
-                const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
-                const double tl = (double)a.tlay[col + (long long)ncol * j];
-                const CellIndex ci = cell_index(m, pu, pl, tl);
-                const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
-                r.c[0] = (Real)(tw0 * pw0); r.c[1] = (Real)(tw0 * ci.pw1);
-                r.c[2] = (Real)(ci.tw1 * pw0); r.c[3] = (Real)(ci.tw1 * ci.pw1);
-                r.ip = ci.ip0 - 1; r.it = ci.it0 - 1; r.iv = 0; r.prow = 0;
+            RecT r;
+            const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
+            const double tl = (double)a.tlay[col + (long long)ncol * j];
+            const CellIndex ci = cell_index(m, pu, pl, tl);
+            const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
+            r.c[0] = (Real)(tw0 * pw0); r.c[1] = (Real)(tw0 * ci.pw1);
+            r.c[2] = (Real)(ci.tw1 * pw0); r.c[3] = (Real)(ci.tw1 * ci.pw1);
+            const int ip = ci.ip0 - 1, it = ci.it0 - 1;
+            r.pk = ip * kNTP + it;
+            // Tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the per-g clamp
+            // (:233-238) becomes "skip the gas when its weight is negative"; NaN weights propagate.
+            int mask = 0;
+            r.w[0] = (Real)ci.sw;
+            if (has_mix) mask |= (ci.sw < 0.0) ? 0x200 : 1;
 #pragma unroll
-                for (int b = 0; b < kMaxBil; ++b) {
-                    Real wv = 0;
-                    if (b < nbil) {
-                        const GasRef &gr = cg.g[cg.bil[b]];
-                        const double vmr = gr.code == kNone ? 0.0 : load_vmr<Real>(gr, col, j);
-                        wv = (Real)gas_weight(gr, ci.sw, vmr);
-                    }
-                    r.w[b] = wv;
+            for (int s = 1; s < NB; ++s) {
+                Real wv = 0;
+                if (s <= nvar) {
+                    const GasRef &gr = cg.g[cg.var_gas[s - 1]];
+                    const double wd = gas_weight(gr, ci.sw, load_vmr<Real>(gr, col, j));
+                    wv = (Real)wd;
+                    if (!(wd < 0.0)) mask |= 1 << s;
                 }
-                r.wl = 0; r.vw1 = 0;
-                if (has_lut) {
-                    const GasRef &gr = cg.g[cg.lut];
-                    const double vmr = load_vmr<Real>(gr, col, j);
-                    double v1;
-                    r.iv = vmr_index(gr, vmr, v1) - 1;
-                    r.vw1 = (Real)v1;
-                    r.wl = (Real)gas_weight(gr, ci.sw, vmr);
-                }
-                r.pa[0] = r.pa[1] = r.pa[2] = r.pa[3] = 0;
-                if (SW) {
-                    r.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
-                } else {
-                    double a0, a1;
-                    int it = planck_index(m, tl, a0, a1);
-                    int rows = max(it, 1) - 1;
-                    r.pa[0] = (Real)__ddiv_rn(a0, m.pi); r.pa[1] = (Real)__ddiv_rn(a1, m.pi);
-                    if (a.tlev) {
-                        it = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
-                        rows |= (max(it, 1) - 1) << 16;
-                        r.pa[2] = (Real)__ddiv_rn(a0, m.pi); r.pa[3] = (Real)__ddiv_rn(a1, m.pi);
-                    }
-                    r.prow = rows;
-                }
-                recs[warp * 32 + lane] = r;
+                r.w[s] = wv;
             }
+            r.wl = 0; r.vw1 = 0; r.hk = 0;
+            if (has_lut) {
+                const GasRef &gr = cg.g[cg.lut];
+                const double vmr = load_vmr<Real>(gr, col, j);
+                double v1;
+                const int iv = vmr_index(gr, vmr, v1) - 1;
+                r.hk = (iv * kNPP + ip) * kNTP + it;
+                r.vw1 = (Real)v1;
+                const double wd = gas_weight(gr, ci.sw, vmr);
+                r.wl = (Real)wd;
+                if (!(wd < 0.0)) mask |= 0x100;
+            }
+            r.mask = mask;
+            r.pa[0] = r.pa[1] = r.pa[2] = r.pa[3] = 0;
+            r.prow = 0;
+            if (SW) {
+                r.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
+            } else {
+                double a0, a1;
+                int itp = planck_index(m, tl, a0, a1);
+                int rows = max(itp, 1) - 1;
+                r.pa[0] = (Real)__ddiv_rn(a0, m.pi); r.pa[1] = (Real)__ddiv_rn(a1, m.pi);
+                if (a.tlev) {
+                    itp = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
+                    rows |= (max(itp, 1) - 1) << 16;
+                    r.pa[2] = (Real)__ddiv_rn(a0, m.pi); r.pa[3] = (Real)__ddiv_rn(a1, m.pi);
+                }
+                r.prow = rows;
+            }
+            recs[warp * 32 + lane] = r;
         }
         __syncwarp();
 
-        // ---- phase B: walk the (up to) 32 layers of this chunk ------------------
-        const int nl_chunk = min(32, nlay - j0);
-        for (int l = 0; l < nl_chunk; ++l) {
+        // ---- phase B: walk the layers of this chunk -----------------------------
+        for (int l = 0; l < len; ++l) {
             const int j = j0 + l;
             const int ls = j % L;
             if (col_ok) {
-                const Rec<Real> *rp = myrecs + l;
-                const int4 ix = *reinterpret_cast<const int4 *>(&rp->ip);
+                const RecT *rp = myrecs + l;
+                const int4 ix = *reinterpret_cast<const int4 *>(&rp->pk);
                 Real c0, c1, c2, c3;
                 lds4<Real>(rp->c, c0, c1, c2, c3);
-                const int ip = ix.x, it = ix.y;
-                const int coff = ngpt * ip + s_t * it;
-                if (ip != cur_ip || it != cur_it) {
-                    const bool shift = (ip == cur_ip + 1) && (it == cur_it);
+                const int mask = ix.w;
+                if (ix.x != cur_pk) {
+                    const bool shift = ix.x == cur_pk + kNTP;      // ip0 advanced by one, it0 unchanged
+                    const int coff = ix.x * kGP;
 #pragma unroll
-                    for (int b = 0; b < kMaxBil; ++b) {
-                        if (b < nbil) {
-                            const Real *k = ktab + (cg.bil_off[b] + coff);
-                            if (shift) { kb[b][0] = kb[b][1]; kb[b][2] = kb[b][3]; }
-                            else { kb[b][0] = k[0]; kb[b][2] = k[s_t]; }
-                            kb[b][1] = k[ngpt]; kb[b][3] = k[s_t + ngpt];
+                    for (int s = 0; s < NB; ++s) {
+                        if (s == 0 ? has_mix : s <= nvar) {
+                            const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + coff;
+                            if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
+                            else { kb[s][0] = k[kC00]; kb[s][2] = k[kC01]; }
+                            kb[s][1] = k[kC10]; kb[s][3] = k[kC11];
                         }
                     }
-                    cur_ip = ip; cur_it = it;
+                    cur_pk = ix.x;
                 }
                 Real tau = 0;
                 if (has_lut) {
-                    const int iv = ix.z;
-                    if (ip != cur_hp || it != cur_ht || iv != cur_hv) {
-                        const Real *k = ktab + (cg.lut_off + coff + s_v * iv);
-                        kh[0] = k[0]; kh[1] = k[ngpt]; kh[2] = k[s_t]; kh[3] = k[s_t + ngpt];
-                        k += s_v;
-                        kh[4] = k[0]; kh[5] = k[ngpt]; kh[6] = k[s_t]; kh[7] = k[s_t + ngpt];
-                        cur_hp = ip; cur_ht = it; cur_hv = iv;
+                    if (ix.y != cur_hk) {
+                        const Real *k = wlut + ix.y * kGP;
+                        kh[0] = k[kC00]; kh[1] = k[kC10]; kh[2] = k[kC01]; kh[3] = k[kC11];
+                        kh[4] = k[kSlab + kC00]; kh[5] = k[kSlab + kC10]; kh[6] = k[kSlab + kC01]; kh[7] = k[kSlab + kC11];
+                        cur_hk = ix.y;
                     }
-                    Real wl, v1;
-                    lds2<Real>(&rp->wl, wl, v1);
-                    if (!(wl < (Real)0)) {
+                    if (mask & 0x100) {
+                        Real wl, v1;
+                        lds2<Real>(&rp->wl, wl, v1);
                         const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
                         const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
                         tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < kMaxBil; b += 2) {
-                    if (b < nbil) {
+                for (int s = 0; s < NB; s += 2) {
+                    if (mask & (3 << s)) {
                         Real w0, w1;
-                        lds2<Real>(&rp->w[b], w0, w1);
-                        // tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the
-                        // per-g clamp (:233-238) is a warp-uniform skip of the whole gas
-                        if (!(w0 < (Real)0))
-                            tau += w0 * (c0 * kb[b][0] + c1 * kb[b][1] + c2 * kb[b][2] + c3 * kb[b][3]);
-                        if (b + 1 < nbil && !(w1 < (Real)0))
-                            tau += w1 * (c0 * kb[b + 1][0] + c1 * kb[b + 1][1] + c2 * kb[b + 1][2] + c3 * kb[b + 1][3]);
+                        lds2<Real>(&rp->w[s], w0, w1);
+                        if (mask & (1 << s))
+                            tau += w0 * (c0 * kb[s][0] + c1 * kb[s][1] + c2 * kb[s][2] + c3 * kb[s][3]);
+                        if (mask & (2 << s))
+                            tau += w1 * (c0 * kb[s + 1][0] + c1 * kb[s + 1][1] + c2 * kb[s + 1][2] + c3 * kb[s + 1][3]);
                     }
+                }
+                if (mask & 0x200) {   // upside-down layer: the negative-factor gases give positive optical depth
+                    const Real *k = wmix + (size_t)ngroups * kSlab + ix.x * kGP;
+                    tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
                 }
                 Real *st = st_mine + (buf * NOUT * L + ls) * ROWS;
                 if (SW) {
@@ -339,9 +382,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 } else {
                     Real p0, p1, p2, p3;
                     lds4<Real>(rp->pa, p0, p1, p2, p3);
-                    const int rl = (ix.w & 0xffff) * ngpt, rv = (ix.w >> 16) * ngpt;
-                    const Real lay_src = p0 * ptab[rl] + p1 * ptab[rl + ngpt];
-                    const Real lev_next = p2 * ptab[rv] + p3 * ptab[rv + ngpt];
+                    const Real *pl = wpl + (ix.z & 0xffff) * kGP, *pv = wpl + (ix.z >> 16) * kGP;
+                    const Real lay_src = p0 * pl[0] + p1 * pl[kGP];
+                    const Real lev_next = p2 * pv[0] + p3 * pv[kGP];
                     st[0] = tau;
                     st[1 * L * ROWS] = lay_src;
                     st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
@@ -353,21 +396,23 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 __syncthreads();
                 if (wo_ok) {
                     const int nl = ls + 1;
-                    const long long off0 = wo_base + (long long)ncol * (j - ls);
+                    const long long off0 = (wo_base + (long long)ncol * (j - ls)) * (long long)sizeof(Real);
+                    const long long pitch = (long long)ncol * (long long)sizeof(Real);
                     const Real *sb = wo_st + buf * NOUT * L * ROWS;
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) {
-                        Real *dst = a.out[o];
-                        if (dst) {
+                        if (a.out[o]) {
+                            char *dst = reinterpret_cast<char *>(a.out[o]) + off0;
 #pragma unroll
                             for (int l2 = 0; l2 < L; ++l2)
-                                if (l2 < nl) store_cs(dst + off0 + (long long)ncol * l2, sb[(o * L + l2) * ROWS]);
+                                if (l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), sb[(o * L + l2) * ROWS]);
                         }
                     }
                     if (SW && a.out[2]) {
+                        char *dst = reinterpret_cast<char *>(a.out[2]) + off0;
 #pragma unroll
                         for (int l2 = 0; l2 < L; ++l2)
-                            if (l2 < nl) store_cs(a.out[2] + off0 + (long long)ncol * l2, (Real)0);   // g = 0  :460
+                            if (l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), (Real)0);   // g = 0  :460
                     }
                 }
                 buf ^= 1;
@@ -382,8 +427,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         } else {
             double a0, a1;
             const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                            // :408-412
-            const int r = max(it, 1) - 1;
-            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * ptab[r * ngpt] + (Real)__ddiv_rn(a1, m.pi) * ptab[(r + 1) * ngpt];
+            const Real *p = wpl + (max(it, 1) - 1) * kGP;
+            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * p[0] + (Real)__ddiv_rn(a1, m.pi) * p[kGP];
         }
     }
 }
@@ -420,23 +465,36 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // ============================================================================
 // launchers
 // ============================================================================
-template <typename Real, bool SW, int TC, int L, int MINB>
-static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
+template <typename Real, bool SW, int NB, int TC, int L, int MINB>
+static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 4;
-    const size_t smem = sizeof(Rec<Real>) * TC * 32 + sizeof(Real) * 2 * NOUT * L * 32 * (TC + 1);
-    auto kern = walk_kernel<Real, SW, TC, L, MINB>;
+    const size_t smem = sizeof(Rec<Real, NB>) * TC * 32 + sizeof(Real) * 2 * NOUT * L * 32 * (TC + 1);
+    auto kern = walk_kernel<Real, SW, NB, TC, L, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + 31) / 32));
-    kern<<<grid, TC * 32, smem, s>>>(m, cg, a);
+    dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
+    kern<<<grid, TC * 32, smem, s>>>(m, cg, a, mix);
     return cudaGetLastError();
 }
 
-template <typename Real, bool SW>
-cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, cudaStream_t s)
+size_t walk_scratch_bytes(const DevModel &m, const CallGases &, size_t real_size)
 {
-    return launch_walk_t<Real, SW, 16, 2, 1>(m, cg, a, s);
+    return (size_t)2 * ((m.ngpt + kGP - 1) / kGP) * kSlab * real_size;
+}
+
+template <typename Real, bool SW>
+cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, void *scratch, cudaStream_t s)
+{
+    Real *mix = static_cast<Real *>(scratch);
+    if (cg.nmix > 0) {
+        const int n = ((m.ngpt + kGP - 1) / kGP) * kSlab;
+        mix_kernel<Real><<<(n + 255) / 256, 256, 0, s>>>(m, cg, mix);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (cg.nvar <= 1) return launch_walk_t<Real, SW, 2, 16, 2, 1>(m, cg, a, mix, s);
+    return launch_walk_t<Real, SW, 8, 16, 2, 1>(m, cg, a, mix, s);
 }
 
 template <typename Real, bool SW>
@@ -466,8 +524,8 @@ cudaError_t launch_planck_indices(const DevModel &m, long long n, const double *
 }
 
 #define ECCKD_INST(Real)                                                                                               \
-    template cudaError_t launch_walk<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t); \
-    template cudaError_t launch_walk<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);  \
+    template cudaError_t launch_walk<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t); \
+    template cudaError_t launch_walk<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t);  \
     template cudaError_t launch_generic<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t); \
     template cudaError_t launch_generic<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);  \
     template cudaError_t launch_indices<Real>(const DevModel &, const GasRef *, int, int, const Real *, const Real *, int *,   \

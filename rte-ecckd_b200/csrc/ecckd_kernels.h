@@ -19,8 +19,11 @@ template <typename Real> struct KernelArgs {
     Real *out2d;
 };
 
+// Bytes of stream-ordered scratch launch_walk needs for the per-call mixed table (0: none).
+size_t walk_scratch_bytes(const DevModel &, const CallGases &, size_t real_size);
+// Launches the table-mixing kernel (when the call has constant-factor gases) and the walking kernel.
 template <typename Real, bool SW>
-cudaError_t launch_walk(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);
+cudaError_t launch_walk(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *scratch, cudaStream_t);
 template <typename Real, bool SW>
 cudaError_t launch_generic(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);
 template <typename Real>

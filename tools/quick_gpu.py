@@ -14,9 +14,12 @@ dev = torch.device("cuda:0")
 def rel(a, b):
     return ge._rel_err(a, b)
 
-def parity(path, ncol, nlay):
+def parity(path, ncol, nlay, all2d=False):
     atm = synthetic.make_atmosphere(ncol, nlay)
-    gl_cpu = [(n, v.numpy() if torch.is_tensor(v) else v) for n, v in atm.gas_list()]
+    glist = atm.gas_list()
+    if all2d:   # every gas as a (ncol, nlay) field with some variation: exercises the NB=8 walk kernel
+        glist = [(n, v if torch.is_tensor(v) else ecckd_b200.to_fortran(v * (1.0 + 0.3 * torch.sin(torch.arange(ncol * nlay, dtype=torch.float64)).reshape(ncol, nlay)), torch.float64)) for n, v in glist]
+    gl_cpu = [(n, v.numpy() if torch.is_tensor(v) else v) for n, v in glist]
     F = lambda t: np.asfortranarray(t.numpy())
     m = ckd_model.load_and_init(path)
     co = COracle(m)
@@ -28,13 +31,13 @@ def parity(path, ncol, nlay):
         ref, _ = co.gas_optics_ext(F(atm.plev), F(atm.tlay), gl_cpu)
     for dt, tol in ((torch.float64, 1e-12), (torch.float32, 1e-5)):
         D = lambda t: ecckd_b200.to_fortran(t, dt, dev)
-        gl = [(n, D(v) if torch.is_tensor(v) else v) for n, v in atm.gas_list()]
+        gl = [(n, D(v) if torch.is_tensor(v) else v) for n, v in glist]
         for kern, kname in ((ecckd_b200.KERNEL_WALK, "walk"), (ecckd_b200.KERNEL_GENERIC, "generic")):
             out = go.gas_optics(None, D(atm.plev), D(atm.tlay), atm.tsfc.to(dev, dt) if lw else None, gl,
                                 tlev=D(atm.tlev) if lw else None, kernel=kern)
             torch.cuda.synchronize()
             errs = {k: rel(out[k].cpu().numpy(), v) for k, v in ref.items()}
-            print(os.path.basename(path)[10:40], str(dt)[6:], kname, "OK" if max(errs.values()) <= tol else "FAIL",
+            print(os.path.basename(path)[10:40], "all2d" if all2d else "", str(dt)[6:], kname, "OK" if max(errs.values()) <= tol else "FAIL",
                   {k: f"{e:.2e}" for k, e in errs.items()}, flush=True)
 
 def timing(path, ncol, nlay, dt, kern, reps=5):
@@ -68,6 +71,7 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     for p in (ge.LW_FILE, ge.LW2_FILE, ge.SW_FILE):
         parity(p, 67, 61)
+        parity(p, 35, 70, all2d=True)
     ncol = int(os.environ.get("NCOL", 65536))
     for p in (ge.LW_FILE, ge.SW_FILE):
         for dt in (torch.float64, torch.float32):
