@@ -21,6 +21,7 @@
 //                     cross-check of walk_kernel in the GPU tests.
 #include "ecckd_device.cuh"
 #include "ecckd_kernels.h"
+#include <cstdlib>
 
 namespace ecckd {
 
@@ -197,28 +198,118 @@ template <> __device__ __forceinline__ void lds2<float>(const float *p, float &a
 // corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
 constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
 
+// ---- mbarrier helpers (shared::cta, generic proxy only) -------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)   // release.cta
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)   // acquire.cta
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <typename Real> __device__ __forceinline__ void prefetch_l1(const Real *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
-template <typename Real, bool SW, int NB, int TC, int L, int MINB>
-__global__ void __launch_bounds__(TC * 32, MINB)
+//
+// Block = TC compute warps (one column each, lanes = g-points) + NWW writer warps.
+// Compute warps fill a ring of NBUF staging tiles [output][layer][g][column] in
+// shared memory; a tile (L layers) is handed to the writer warps through an
+// mbarrier pair (full/empty), so compute warps never wait for each other, only
+// for a free tile.  Writer warps turn each tile into full-line, column-contiguous
+// streaming stores.
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NWW>
+__global__ void __launch_bounds__((TC + NWW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab)
 {
-    constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled at write-out
+    constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled by the writers
     constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
+    constexpr int TILE = NOUT * L * ROWS; // one ring entry
     using RecT = Rec<Real, NB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RecT *recs = reinterpret_cast<RecT *>(smem_raw);
     Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * TC * 32);
+    unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(stage + (size_t)NBUF * TILE);
+    unsigned long long *bar_empty = bar_full + NBUF;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
     const long long col0 = (long long)blockIdx.x * TC;
-    const long long col = col0 + warp;
-    const bool col_ok = col < ncol;
     const int ngpt = m.ngpt;
     const int grp = blockIdx.y, g0 = grp * kGP;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], NWW); }
+    }
+    __syncthreads();
+
+    // =========================== writer warps ====================================
+    if (warp >= TC) {
+        constexpr int NWT = NWW * 32;                 // writer threads
+        constexpr int GSTEP = NWT / TC;               // g-points covered per pass
+        const int t = threadIdx.x - TC * 32;
+        const int c = t % TC, gsub = t / TC;
+        const bool c_ok = col0 + c < ncol;
+        const long long plane = (long long)ncol * nlay * (long long)sizeof(Real);   // bytes between g-points
+        const long long pitch = (long long)ncol * (long long)sizeof(Real);          // bytes between layers
+        const int nchunk = (nlay + L - 1) / L;
+        for (int n = 0; n < nchunk; ++n) {
+            const int b = n % NBUF, u = n / NBUF;
+            const int lay0 = n * L, nl = min(L, nlay - lay0);
+            mbar_wait(&bar_full[b], u & 1);
+            const Real *sb = stage + (size_t)b * TILE + c;
+            const long long off0 = ((col0 + c) + (long long)ncol * lay0) * (long long)sizeof(Real) + plane * (g0 + gsub);
+            if (c_ok) {
+#pragma unroll 2
+                for (int gi = 0; gi < 32 / GSTEP; ++gi) {
+                    const int gg = gsub + gi * GSTEP;
+                    if (g0 + gg < ngpt) {
+                        Real v[NOUT * L];
+#pragma unroll
+                        for (int q = 0; q < NOUT * L; ++q) v[q] = sb[q * ROWS + gg * TCP];
+                        const long long off = off0 + plane * (gi * GSTEP);
+#pragma unroll
+                        for (int o = 0; o < NOUT; ++o) {
+                            char *dst = reinterpret_cast<char *>(a.out[o]) + off;
+#pragma unroll
+                            for (int l2 = 0; l2 < L; ++l2)
+                                if (a.out[o] && l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), v[o * L + l2]);
+                        }
+                        if (SW && a.out[2]) {
+                            char *dst = reinterpret_cast<char *>(a.out[2]) + off;
+#pragma unroll
+                            for (int l2 = 0; l2 < L; ++l2)
+                                if (l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), (Real)0);   // g = 0  :460
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[b]);
+        }
+        return;
+    }
+
+    // =========================== compute warps ===================================
+    const long long col = col0 + warp;
+    const bool col_ok = col < ncol;
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
     const int nvar = cg.nvar;
     const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
@@ -236,6 +327,30 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     for (int i = 0; i < 8; ++i) kh[i] = 0;
     int cur_pk = -0x10000, cur_hk = -0x10000;
 
+    // (re)load the register cache for corner keys (pk, hk); no-ops when unchanged
+    auto refill = [&](int pk, int hk) {
+        if (pk != cur_pk) {
+            const bool shift = pk == cur_pk + kNTP;      // ip0 advanced by one, it0 unchanged
+            const int coff = pk * kGP;
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                if (s == 0 ? has_mix : s <= nvar) {
+                    const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + coff;
+                    if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
+                    else { kb[s][0] = k[kC00]; kb[s][2] = k[kC01]; }
+                    kb[s][1] = k[kC10]; kb[s][3] = k[kC11];
+                }
+            }
+            cur_pk = pk;
+        }
+        if (has_lut && hk != cur_hk) {
+            const Real *k = wlut + hk * kGP;
+            kh[0] = k[kC00]; kh[1] = k[kC10]; kh[2] = k[kC01]; kh[3] = k[kC11];
+            kh[4] = k[kSlab + kC00]; kh[5] = k[kSlab + kC10]; kh[6] = k[kSlab + kC01]; kh[7] = k[kSlab + kC11];
+            cur_hk = hk;
+        }
+    };
+
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
     Real lev_prev = 0;   // Planck source at the upper level of the current layer
     if (!SW && col_ok && a.tlev) {
@@ -245,15 +360,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         lev_prev = (Real)__ddiv_rn(a0, m.pi) * p[0] + (Real)__ddiv_rn(a1, m.pi) * p[kGP];
     }
 
-    // per-thread constants of the staging tile and of the cooperative write-out
     const RecT *myrecs = recs + warp * 32;
-    Real *st_mine = stage + lane * TCP + warp;             // + (buf*NOUT*L + o*L + ls) * ROWS
-    const int wo_c = threadIdx.x % TC, wo_g = threadIdx.x / TC;
-    const bool wo_ok = (g0 + wo_g < ngpt) && (col0 + wo_c < ncol);
-    const long long wo_base = (col0 + wo_c) + (long long)ncol * nlay * (g0 + wo_g);
-    const Real *wo_st = stage + wo_g * TCP + wo_c;
+    Real *st_mine = stage + lane * TCP + warp;             // + b*TILE + (o*L + ls)*ROWS
 
-    int buf = 0;
     for (int j0 = 0; j0 < nlay; j0 += 32) {
         const int len = min(32, nlay - j0);
         // ---- phase A: lane l computes the record of layer j0 + l ----------------
@@ -317,46 +426,38 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             recs[warp * 32 + lane] = r;
         }
         __syncwarp();
+        // pull the next chunk's inputs towards L1 while this chunk is walked
+        if (col_ok && j0 + 32 + lane < nlay) {
+            const long long o = col + (long long)ncol * (j0 + 32 + lane);
+            prefetch_l1(a.plev + o + ncol);
+            prefetch_l1(a.tlay + o);
+            if (!SW && a.tlev) prefetch_l1(a.tlev + o + ncol);
+            if (has_lut) {
+                const GasRef &gr = cg.g[cg.lut];
+                prefetch_l1(static_cast<const Real *>(gr.vmr) + col * gr.col_stride + (long long)(j0 + 32 + lane) * gr.lay_stride);
+            }
+        }
 
         // ---- phase B: walk the layers of this chunk -----------------------------
+        if (col_ok) refill(myrecs[0].pk, myrecs[0].hk);
         for (int l = 0; l < len; ++l) {
             const int j = j0 + l;
-            const int ls = j % L;
+            const int n = j / L, ls = j % L;
+            const int b = n % NBUF;
+            if (ls == 0 && n >= NBUF) mbar_wait(&bar_empty[b], ((n / NBUF) - 1) & 1);   // tile free again?
             if (col_ok) {
                 const RecT *rp = myrecs + l;
                 const int4 ix = *reinterpret_cast<const int4 *>(&rp->pk);
                 Real c0, c1, c2, c3;
                 lds4<Real>(rp->c, c0, c1, c2, c3);
                 const int mask = ix.w;
-                if (ix.x != cur_pk) {
-                    const bool shift = ix.x == cur_pk + kNTP;      // ip0 advanced by one, it0 unchanged
-                    const int coff = ix.x * kGP;
-#pragma unroll
-                    for (int s = 0; s < NB; ++s) {
-                        if (s == 0 ? has_mix : s <= nvar) {
-                            const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + coff;
-                            if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
-                            else { kb[s][0] = k[kC00]; kb[s][2] = k[kC01]; }
-                            kb[s][1] = k[kC10]; kb[s][3] = k[kC11];
-                        }
-                    }
-                    cur_pk = ix.x;
-                }
                 Real tau = 0;
-                if (has_lut) {
-                    if (ix.y != cur_hk) {
-                        const Real *k = wlut + ix.y * kGP;
-                        kh[0] = k[kC00]; kh[1] = k[kC10]; kh[2] = k[kC01]; kh[3] = k[kC11];
-                        kh[4] = k[kSlab + kC00]; kh[5] = k[kSlab + kC10]; kh[6] = k[kSlab + kC01]; kh[7] = k[kSlab + kC11];
-                        cur_hk = ix.y;
-                    }
-                    if (mask & 0x100) {
-                        Real wl, v1;
-                        lds2<Real>(&rp->wl, wl, v1);
-                        const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
-                        const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
-                        tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
-                    }
+                if (mask & 0x100) {
+                    Real wl, v1;
+                    lds2<Real>(&rp->wl, wl, v1);
+                    const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
+                    const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
+                    tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
                 }
 #pragma unroll
                 for (int s = 0; s < NB; s += 2) {
@@ -373,7 +474,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     const Real *k = wmix + (size_t)ngroups * kSlab + ix.x * kGP;
                     tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
                 }
-                Real *st = st_mine + (buf * NOUT * L + ls) * ROWS;
+                // the cache is free now: start fetching the corners of the next layer so that
+                // their latency overlaps the Planck / staging work below
+                if (l + 1 < len) refill(rp[1].pk, rp[1].hk);
+                Real *st = st_mine + b * TILE + ls * ROWS;
                 if (SW) {
                     const Real ray = rp->pa[0] * sigma;             // :313-316
                     tau += ray;                                     // :456
@@ -393,29 +497,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
             }
             if (ls == L - 1 || j == nlay - 1) {
-                __syncthreads();
-                if (wo_ok) {
-                    const int nl = ls + 1;
-                    const long long off0 = (wo_base + (long long)ncol * (j - ls)) * (long long)sizeof(Real);
-                    const long long pitch = (long long)ncol * (long long)sizeof(Real);
-                    const Real *sb = wo_st + buf * NOUT * L * ROWS;
-#pragma unroll
-                    for (int o = 0; o < NOUT; ++o) {
-                        if (a.out[o]) {
-                            char *dst = reinterpret_cast<char *>(a.out[o]) + off0;
-#pragma unroll
-                            for (int l2 = 0; l2 < L; ++l2)
-                                if (l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), sb[(o * L + l2) * ROWS]);
-                        }
-                    }
-                    if (SW && a.out[2]) {
-                        char *dst = reinterpret_cast<char *>(a.out[2]) + off0;
-#pragma unroll
-                        for (int l2 = 0; l2 < L; ++l2)
-                            if (l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), (Real)0);   // g = 0  :460
-                    }
-                }
-                buf ^= 1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[b]);
             }
         }
     }
@@ -465,16 +548,16 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // ============================================================================
 // launchers
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int MINB>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NWW>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 4;
-    const size_t smem = sizeof(Rec<Real, NB>) * TC * 32 + sizeof(Real) * 2 * NOUT * L * 32 * (TC + 1);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, MINB>;
+    const size_t smem = sizeof(Rec<Real, NB>) * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * (TC + 1) + 2 * NBUF * sizeof(unsigned long long);
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NWW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
-    kern<<<grid, TC * 32, smem, s>>>(m, cg, a, mix);
+    kern<<<grid, (TC + NWW) * 32, smem, s>>>(m, cg, a, mix);
     return cudaGetLastError();
 }
 
@@ -493,8 +576,23 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    if (cg.nvar <= 1) return launch_walk_t<Real, SW, 2, 16, 2, 1>(m, cg, a, mix, s);
-    return launch_walk_t<Real, SW, 8, 16, 2, 1>(m, cg, a, mix, s);
+    if (cg.nvar <= 1) {
+#ifdef ECCKD_TUNE
+        static const int variant = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+        switch (variant) {   // NB, TC, L, NBUF, NWW
+            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 3, 4>(m, cg, a, mix, s);
+            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 4, 2>(m, cg, a, mix, s);
+            case 3: return launch_walk_t<Real, SW, 2, 16, 4, 2, 2>(m, cg, a, mix, s);
+            case 4: return launch_walk_t<Real, SW, 2, 16, 1, 6, 2>(m, cg, a, mix, s);
+            case 5: return launch_walk_t<Real, SW, 2, 8, 2, 3, 1>(m, cg, a, mix, s);
+            case 6: return launch_walk_t<Real, SW, 2, 8, 4, 3, 1>(m, cg, a, mix, s);
+            case 7: return launch_walk_t<Real, SW, 2, 16, 2, 2, 2>(m, cg, a, mix, s);
+            default: break;
+        }
+#endif
+        return launch_walk_t<Real, SW, 2, 16, 2, 3, 2>(m, cg, a, mix, s);
+    }
+    return launch_walk_t<Real, SW, 8, 8, 2, 3, 1>(m, cg, a, mix, s);
 }
 
 template <typename Real, bool SW>
