@@ -492,7 +492,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
                     for (int r = 0; r < t->nplanck; ++r)
                         for (int ln = 0; ln < kGP; ++ln)
                             if (grp * kGP + ln < ng)
-                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln];
+                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln] / (double)3.14159265359f;   // :288, folded into the table
             }
         }
         M->nslot_ = nslot; M->nv_lut_ = lut_gas >= 0 ? M->nv[lut_gas] : 0;

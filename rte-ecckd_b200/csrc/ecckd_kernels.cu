@@ -158,19 +158,21 @@ mix_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases
 }
 
 // ---- records ------------------------------------------------------------------
-// Per-(warp, layer) record produced by the lane-distributed index phase and read
-// back as warp-wide broadcasts (every lane reads the same address: one wavefront
-// per 16-byte vector load).  Field groups are 16-byte aligned for both real kinds.
+// Per-(column, layer) record produced by the index warps and read back by the
+// compute warp of that column as warp-wide broadcasts (every lane reads the same
+// address: one wavefront per 16-byte vector load).
 template <typename Real, int NB> struct alignas(16) Rec {
     Real c[4];          // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
-    Real pa[4];         // LW: lay (a0,a1)/pi, lower level (a0,a1)/pi.  SW: pa[0] = moles_per_layer
+    Real pa[4];         // LW: lay (a0,a1), lower level (a0,a1) [table is pre-divided by pi].  SW: pa[0] = moles_per_layer
     Real w[NB];         // w[0] = simple_weight (mixed table); w[s] = weight of varying gas s-1
     Real wl, vw1;       // LUT gas: weight, vmr_weight1
-    alignas(16) int pk; // bilinear corner key  ip*kNTP + it          (0-based ip, it)
-    int hk;             // LUT corner key       (iv*kNPP + ip)*kNTP + it
-    int prow;           // Planck rows: lay_row | lev_row << 16
-    int mask;           // bit s: slot s contributes; bit 8: LUT gas; bit 9: negative-weight mix (slow path)
+    alignas(16) int key;// bilinear corner offset (ip*kNTP + it)*kGP  |  mask << 16
+                        //   mask bit s: slot s contributes; bit 8: LUT gas; bit 9: negative-weight mix (slow path)
+    int hkoff;          // LUT corner offset ((iv*kNPP + ip)*kNTP + it)*kGP
+    int lay_off;        // Planck row offset of the layer temperature      (row*kGP)
+    int lev_off;        // Planck row offset of the lower-level temperature
 };
+constexpr int kMaskShift = 16, kMaskLut = 0x100 << kMaskShift, kMaskNeg = 0x200 << kMaskShift;
 
 template <typename Real> __device__ __forceinline__ void lds4(const Real *p, Real &a, Real &b, Real &c, Real &d);
 template <> __device__ __forceinline__ void lds4<double>(const double *p, double &a, double &b, double &c, double &d)
@@ -218,22 +220,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-template <typename Real> __device__ __forceinline__ void prefetch_l1(const Real *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 
+// ============================================================================
+// walk_kernel: a three-role, warp-specialised pipeline inside one block
+//
+//   index warps   (NI)  lane l computes the interpolation record of layer j0+l of
+//                       one column: log-pressure / temperature / mole-fraction /
+//                       Planck indices and weights -- long dependent chains (log,
+//                       IEEE divisions), one chunk of 32 layers ahead of the walk
+//   compute warps (TC)  one column each, lanes = g-points: walk the layers top to
+//                       bottom, corner rows cached in registers, accumulate tau and
+//                       the sources, write them transposed into a ring of staging
+//                       tiles [output][layer][g][column]
+//   writer warps  (NWW) turn finished tiles into full-line, column-contiguous
+//                       streaming stores
+//
+// Hand-offs are mbarrier full/empty pairs, so no role ever waits for a peer of
+// the same role: index -> compute through double-buffered per-column record
+// chunks, compute -> writer through NBUF tiles of L layers.
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
-//
-// Block = TC compute warps (one column each, lanes = g-points) + NWW writer warps.
-// Compute warps fill a ring of NBUF staging tiles [output][layer][g][column] in
-// shared memory; a tile (L layers) is handed to the writer warps through an
-// mbarrier pair (full/empty), so compute warps never wait for each other, only
-// for a free tile.  Writer warps turn each tile into full-line, column-contiguous
-// streaming stores.
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NWW>
-__global__ void __launch_bounds__((TC + NWW) * 32, 1)
+// ============================================================================
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW>
+__global__ void __launch_bounds__((TC + NI + NWW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab)
 {
@@ -241,30 +250,37 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
     constexpr int TILE = NOUT * L * ROWS; // one ring entry
+    static_assert(TC % NI == 0, "every index warp serves TC/NI columns");
     using RecT = Rec<Real, NB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RecT *recs = reinterpret_cast<RecT *>(smem_raw);
-    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * TC * 32);
+    RecT *recs = reinterpret_cast<RecT *>(smem_raw);                                  // [2][TC][32]
+    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * 2 * TC * 32);     // [NBUF][TILE]
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(stage + (size_t)NBUF * TILE);
     unsigned long long *bar_empty = bar_full + NBUF;
+    unsigned long long *rec_full = bar_empty + NBUF;       // [2][TC]
+    unsigned long long *rec_empty = rec_full + 2 * TC;     // [2][TC]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
     const long long col0 = (long long)blockIdx.x * TC;
     const int ngpt = m.ngpt;
     const int grp = blockIdx.y, g0 = grp * kGP;
+    const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
+    const int nvar = cg.nvar;
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], NWW); }
+        for (int q = 0; q < 2 * TC; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], 1); }
     }
     __syncthreads();
+    const int nround = (nlay + 31) / 32;
 
     // =========================== writer warps ====================================
-    if (warp >= TC) {
+    if (warp >= TC + NI) {
         constexpr int NWT = NWW * 32;                 // writer threads
         constexpr int GSTEP = NWT / TC;               // g-points covered per pass
-        const int t = threadIdx.x - TC * 32;
+        const int t = threadIdx.x - (TC + NI) * 32;
         const int c = t % TC, gsub = t / TC;
         const bool c_ok = col0 + c < ncol;
         const long long plane = (long long)ncol * nlay * (long long)sizeof(Real);   // bytes between g-points
@@ -307,12 +323,81 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         return;
     }
 
+    // =========================== index warps =====================================
+    if (warp >= TC) {
+        const int iw = warp - TC;
+        for (int r = 0; r < nround; ++r) {
+            const int rb = r & 1, u = r >> 1;
+            const int j = r * 32 + lane;
+            for (int cs = iw; cs < TC; cs += NI) {
+                const long long col = min(col0 + cs, (long long)ncol - 1);   // tail tiles recompute the last column; never stored
+                RecT rec;
+                if (j < nlay) {
+                    const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
+                    const double tl = (double)a.tlay[col + (long long)ncol * j];
+                    const CellIndex ci = cell_index(m, pu, pl, tl);
+                    const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
+                    rec.c[0] = (Real)(tw0 * pw0); rec.c[1] = (Real)(tw0 * ci.pw1);
+                    rec.c[2] = (Real)(ci.tw1 * pw0); rec.c[3] = (Real)(ci.tw1 * ci.pw1);
+                    const int ip = ci.ip0 - 1, it = ci.it0 - 1;
+                    // Tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the per-g clamp
+                    // (:233-238) becomes "skip the gas when its weight is negative"; NaN weights propagate.
+                    int mask = 0;
+                    rec.w[0] = (Real)ci.sw;
+                    if (has_mix) mask |= (ci.sw < 0.0) ? 0x200 : 1;
+#pragma unroll
+                    for (int s = 1; s < NB; ++s) {
+                        Real wv = 0;
+                        if (s <= nvar) {
+                            const GasRef &gr = cg.g[cg.var_gas[s - 1]];
+                            const double wd = gas_weight(gr, ci.sw, load_vmr<Real>(gr, col, j));
+                            wv = (Real)wd;
+                            if (!(wd < 0.0)) mask |= 1 << s;
+                        }
+                        rec.w[s] = wv;
+                    }
+                    rec.wl = 0; rec.vw1 = 0; rec.hkoff = 0;
+                    if (has_lut) {
+                        const GasRef &gr = cg.g[cg.lut];
+                        const double vmr = load_vmr<Real>(gr, col, j);
+                        double v1;
+                        const int iv = vmr_index(gr, vmr, v1) - 1;
+                        rec.hkoff = ((iv * kNPP + ip) * kNTP + it) * kGP;
+                        rec.vw1 = (Real)v1;
+                        const double wd = gas_weight(gr, ci.sw, vmr);
+                        rec.wl = (Real)wd;
+                        if (!(wd < 0.0)) mask |= 0x100;
+                    }
+                    rec.key = (ip * kNTP + it) * kGP | mask << kMaskShift;
+                    rec.pa[0] = rec.pa[1] = rec.pa[2] = rec.pa[3] = 0;
+                    rec.lay_off = rec.lev_off = 0;
+                    if (SW) {
+                        rec.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
+                    } else {
+                        double a0, a1;
+                        int itp = planck_index(m, tl, a0, a1);
+                        rec.lay_off = (max(itp, 1) - 1) * kGP;
+                        rec.pa[0] = (Real)a0; rec.pa[1] = (Real)a1;
+                        if (a.tlev) {
+                            itp = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
+                            rec.lev_off = (max(itp, 1) - 1) * kGP;
+                            rec.pa[2] = (Real)a0; rec.pa[3] = (Real)a1;
+                        }
+                    }
+                }
+                if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
+                if (j < nlay) recs[(rb * TC + cs) * 32 + lane] = rec;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rec_full[rb * TC + cs]);
+            }
+        }
+        return;
+    }
+
     // =========================== compute warps ===================================
-    const long long col = col0 + warp;
-    const bool col_ok = col < ncol;
+    const long long col = min(col0 + warp, (long long)ncol - 1);
+    const bool col_ok = col0 + warp < ncol;
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
-    const int nvar = cg.nvar;
-    const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
     const int ngroups = gridDim.y;
     const Real *wbil = TableOf<Real>::wbil(m) + (size_t)grp * m.nslot * kSlab + lane;
     const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
@@ -327,180 +412,112 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     for (int i = 0; i < 8; ++i) kh[i] = 0;
     int cur_pk = -0x10000, cur_hk = -0x10000;
 
-    // (re)load the register cache for corner keys (pk, hk); no-ops when unchanged
-    auto refill = [&](int pk, int hk) {
-        if (pk != cur_pk) {
-            const bool shift = pk == cur_pk + kNTP;      // ip0 advanced by one, it0 unchanged
-            const int coff = pk * kGP;
+    // (re)load the register cache for corner offsets (pkoff, hkoff); no-ops when unchanged
+    auto refill = [&](int pkoff, int hkoff) {
+        if (pkoff != cur_pk) {
+            const bool shift = pkoff == cur_pk + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
 #pragma unroll
             for (int s = 0; s < NB; ++s) {
                 if (s == 0 ? has_mix : s <= nvar) {
-                    const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + coff;
+                    const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + pkoff;
                     if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
                     else { kb[s][0] = k[kC00]; kb[s][2] = k[kC01]; }
                     kb[s][1] = k[kC10]; kb[s][3] = k[kC11];
                 }
             }
-            cur_pk = pk;
+            cur_pk = pkoff;
         }
-        if (has_lut && hk != cur_hk) {
-            const Real *k = wlut + hk * kGP;
+        if (has_lut && hkoff != cur_hk) {
+            const Real *k = wlut + hkoff;
             kh[0] = k[kC00]; kh[1] = k[kC10]; kh[2] = k[kC01]; kh[3] = k[kC11];
             kh[4] = k[kSlab + kC00]; kh[5] = k[kSlab + kC10]; kh[6] = k[kSlab + kC01]; kh[7] = k[kSlab + kC11];
-            cur_hk = hk;
+            cur_hk = hkoff;
         }
     };
 
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
     Real lev_prev = 0;   // Planck source at the upper level of the current layer
-    if (!SW && col_ok && a.tlev) {
+    if (!SW && a.tlev) {
         double a0, a1;
         const int it = planck_index(m, (double)a.tlev[col], a0, a1);
         const Real *p = wpl + (max(it, 1) - 1) * kGP;
-        lev_prev = (Real)__ddiv_rn(a0, m.pi) * p[0] + (Real)__ddiv_rn(a1, m.pi) * p[kGP];
+        lev_prev = (Real)a0 * p[0] + (Real)a1 * p[kGP];
     }
 
-    const RecT *myrecs = recs + warp * 32;
-    Real *st_mine = stage + lane * TCP + warp;             // + b*TILE + (o*L + ls)*ROWS
-
-    for (int j0 = 0; j0 < nlay; j0 += 32) {
-        const int len = min(32, nlay - j0);
-        // ---- phase A: lane l computes the record of layer j0 + l ----------------
-        __syncwarp();
-        if (col_ok && lane < len) {
-            const int j = j0 + lane;
-            RecT r;
-            const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
-            const double tl = (double)a.tlay[col + (long long)ncol * j];
-            const CellIndex ci = cell_index(m, pu, pl, tl);
-            const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
-            r.c[0] = (Real)(tw0 * pw0); r.c[1] = (Real)(tw0 * ci.pw1);
-            r.c[2] = (Real)(ci.tw1 * pw0); r.c[3] = (Real)(ci.tw1 * ci.pw1);
-            const int ip = ci.ip0 - 1, it = ci.it0 - 1;
-            r.pk = ip * kNTP + it;
-            // Tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the per-g clamp
-            // (:233-238) becomes "skip the gas when its weight is negative"; NaN weights propagate.
-            int mask = 0;
-            r.w[0] = (Real)ci.sw;
-            if (has_mix) mask |= (ci.sw < 0.0) ? 0x200 : 1;
+    Real *st = stage + lane * TCP + warp;      // running staging pointer of this thread: + b*TILE + ls*ROWS
+    int ls = 0, b = 0, fill = 0;               // layer inside the tile, ring slot, fills of slot 0 so far
+    for (int r = 0; r < nround; ++r) {
+        const int rb = r & 1;
+        const int len = min(32, nlay - r * 32);
+        mbar_wait(&rec_full[rb * TC + warp], (r >> 1) & 1);
+        const RecT *rp = recs + (rb * TC + warp) * 32;
+        {
+            const int2 k0 = *reinterpret_cast<const int2 *>(&rp->key);
+            refill(k0.x & 0xffff, k0.y);
+        }
+        for (int l = 0; l < len; ++l, ++rp) {
+            if (ls == 0 && fill >= 1) mbar_wait(&bar_empty[b], (fill - 1) & 1);   // tile free again?
+            const int4 ix = *reinterpret_cast<const int4 *>(&rp->key);
+            Real c0, c1, c2, c3;
+            lds4<Real>(rp->c, c0, c1, c2, c3);
+            const int key = ix.x;
+            Real tau = 0;
+            if (key & kMaskLut) {
+                Real wl, v1;
+                lds2<Real>(&rp->wl, wl, v1);
+                const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
+                const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
+                tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
+            }
 #pragma unroll
-            for (int s = 1; s < NB; ++s) {
-                Real wv = 0;
-                if (s <= nvar) {
-                    const GasRef &gr = cg.g[cg.var_gas[s - 1]];
-                    const double wd = gas_weight(gr, ci.sw, load_vmr<Real>(gr, col, j));
-                    wv = (Real)wd;
-                    if (!(wd < 0.0)) mask |= 1 << s;
+            for (int s = 0; s < NB; s += 2) {
+                if (key & (3 << (s + kMaskShift))) {
+                    Real w0, w1;
+                    lds2<Real>(&rp->w[s], w0, w1);
+                    if (key & (1 << (s + kMaskShift)))
+                        tau += w0 * (c0 * kb[s][0] + c1 * kb[s][1] + c2 * kb[s][2] + c3 * kb[s][3]);
+                    if (key & (2 << (s + kMaskShift)))
+                        tau += w1 * (c0 * kb[s + 1][0] + c1 * kb[s + 1][1] + c2 * kb[s + 1][2] + c3 * kb[s + 1][3]);
                 }
-                r.w[s] = wv;
             }
-            r.wl = 0; r.vw1 = 0; r.hk = 0;
-            if (has_lut) {
-                const GasRef &gr = cg.g[cg.lut];
-                const double vmr = load_vmr<Real>(gr, col, j);
-                double v1;
-                const int iv = vmr_index(gr, vmr, v1) - 1;
-                r.hk = (iv * kNPP + ip) * kNTP + it;
-                r.vw1 = (Real)v1;
-                const double wd = gas_weight(gr, ci.sw, vmr);
-                r.wl = (Real)wd;
-                if (!(wd < 0.0)) mask |= 0x100;
+            if (key & kMaskNeg) {   // upside-down layer: the negative-factor gases give positive optical depth
+                const Real *k = wmix + (size_t)ngroups * kSlab + (key & 0xffff);
+                tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
             }
-            r.mask = mask;
-            r.pa[0] = r.pa[1] = r.pa[2] = r.pa[3] = 0;
-            r.prow = 0;
+            // the cache is free now: start fetching the corners of the next layer so that
+            // their latency overlaps the Planck / staging work below
+            if (l + 1 < len) {
+                const int2 k1 = *reinterpret_cast<const int2 *>(&rp[1].key);
+                refill(k1.x & 0xffff, k1.y);
+            }
             if (SW) {
-                r.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
+                const Real ray = rp->pa[0] * sigma;             // :313-316
+                tau += ray;                                     // :456
+                st[0] = tau;
+                st[L * ROWS] = ray / tau;                       // :459
             } else {
-                double a0, a1;
-                int itp = planck_index(m, tl, a0, a1);
-                int rows = max(itp, 1) - 1;
-                r.pa[0] = (Real)__ddiv_rn(a0, m.pi); r.pa[1] = (Real)__ddiv_rn(a1, m.pi);
-                if (a.tlev) {
-                    itp = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
-                    rows |= (max(itp, 1) - 1) << 16;
-                    r.pa[2] = (Real)__ddiv_rn(a0, m.pi); r.pa[3] = (Real)__ddiv_rn(a1, m.pi);
-                }
-                r.prow = rows;
+                Real p0, p1, p2, p3;
+                lds4<Real>(rp->pa, p0, p1, p2, p3);
+                const Real *pl = wpl + ix.z, *pv = wpl + ix.w;
+                const Real lay_src = p0 * pl[0] + p1 * pl[kGP];
+                const Real lev_next = p2 * pv[0] + p3 * pv[kGP];
+                st[0] = tau;
+                st[1 * L * ROWS] = lay_src;
+                st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
+                st[3 * L * ROWS] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
+                lev_prev = lev_next;
             }
-            recs[warp * 32 + lane] = r;
-        }
-        __syncwarp();
-        // pull the next chunk's inputs towards L1 while this chunk is walked
-        if (col_ok && j0 + 32 + lane < nlay) {
-            const long long o = col + (long long)ncol * (j0 + 32 + lane);
-            prefetch_l1(a.plev + o + ncol);
-            prefetch_l1(a.tlay + o);
-            if (!SW && a.tlev) prefetch_l1(a.tlev + o + ncol);
-            if (has_lut) {
-                const GasRef &gr = cg.g[cg.lut];
-                prefetch_l1(static_cast<const Real *>(gr.vmr) + col * gr.col_stride + (long long)(j0 + 32 + lane) * gr.lay_stride);
-            }
-        }
-
-        // ---- phase B: walk the layers of this chunk -----------------------------
-        if (col_ok) refill(myrecs[0].pk, myrecs[0].hk);
-        for (int l = 0; l < len; ++l) {
-            const int j = j0 + l;
-            const int n = j / L, ls = j % L;
-            const int b = n % NBUF;
-            if (ls == 0 && n >= NBUF) mbar_wait(&bar_empty[b], ((n / NBUF) - 1) & 1);   // tile free again?
-            if (col_ok) {
-                const RecT *rp = myrecs + l;
-                const int4 ix = *reinterpret_cast<const int4 *>(&rp->pk);
-                Real c0, c1, c2, c3;
-                lds4<Real>(rp->c, c0, c1, c2, c3);
-                const int mask = ix.w;
-                Real tau = 0;
-                if (mask & 0x100) {
-                    Real wl, v1;
-                    lds2<Real>(&rp->wl, wl, v1);
-                    const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
-                    const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
-                    tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
-                }
-#pragma unroll
-                for (int s = 0; s < NB; s += 2) {
-                    if (mask & (3 << s)) {
-                        Real w0, w1;
-                        lds2<Real>(&rp->w[s], w0, w1);
-                        if (mask & (1 << s))
-                            tau += w0 * (c0 * kb[s][0] + c1 * kb[s][1] + c2 * kb[s][2] + c3 * kb[s][3]);
-                        if (mask & (2 << s))
-                            tau += w1 * (c0 * kb[s + 1][0] + c1 * kb[s + 1][1] + c2 * kb[s + 1][2] + c3 * kb[s + 1][3]);
-                    }
-                }
-                if (mask & 0x200) {   // upside-down layer: the negative-factor gases give positive optical depth
-                    const Real *k = wmix + (size_t)ngroups * kSlab + ix.x * kGP;
-                    tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
-                }
-                // the cache is free now: start fetching the corners of the next layer so that
-                // their latency overlaps the Planck / staging work below
-                if (l + 1 < len) refill(rp[1].pk, rp[1].hk);
-                Real *st = st_mine + b * TILE + ls * ROWS;
-                if (SW) {
-                    const Real ray = rp->pa[0] * sigma;             // :313-316
-                    tau += ray;                                     // :456
-                    st[0] = tau;
-                    st[L * ROWS] = ray / tau;                       // :459
-                } else {
-                    Real p0, p1, p2, p3;
-                    lds4<Real>(rp->pa, p0, p1, p2, p3);
-                    const Real *pl = wpl + (ix.z & 0xffff) * kGP, *pv = wpl + (ix.z >> 16) * kGP;
-                    const Real lay_src = p0 * pl[0] + p1 * pl[kGP];
-                    const Real lev_next = p2 * pv[0] + p3 * pv[kGP];
-                    st[0] = tau;
-                    st[1 * L * ROWS] = lay_src;
-                    st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
-                    st[3 * L * ROWS] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
-                    lev_prev = lev_next;
-                }
-            }
-            if (ls == L - 1 || j == nlay - 1) {
+            st += ROWS;
+            if (++ls == L || (r == nround - 1 && l == len - 1)) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[b]);
+                st += TILE - ls * ROWS;
+                ls = 0;
+                if (++b == NBUF) { b = 0; st -= NBUF * TILE; ++fill; }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rec_empty[rb * TC + warp]);
     }
 
     // ---- per-column 2-D outputs -------------------------------------------------
@@ -511,7 +528,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             double a0, a1;
             const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                            // :408-412
             const Real *p = wpl + (max(it, 1) - 1) * kGP;
-            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * p[0] + (Real)__ddiv_rn(a1, m.pi) * p[kGP];
+            a.out2d[col + (long long)ncol * g] = (Real)a0 * p[0] + (Real)a1 * p[kGP];
         }
     }
 }
@@ -548,16 +565,17 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // ============================================================================
 // launchers
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NWW>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 4;
-    const size_t smem = sizeof(Rec<Real, NB>) * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * (TC + 1) + 2 * NBUF * sizeof(unsigned long long);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NWW>;
+    const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * (TC + 1) +
+                        (2 * NBUF + 4 * TC) * sizeof(unsigned long long);
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
-    kern<<<grid, (TC + NWW) * 32, smem, s>>>(m, cg, a, mix);
+    kern<<<grid, (TC + NI + NWW) * 32, smem, s>>>(m, cg, a, mix);
     return cudaGetLastError();
 }
 
@@ -579,20 +597,20 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
     if (cg.nvar <= 1) {
 #ifdef ECCKD_TUNE
         static const int variant = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
-        switch (variant) {   // NB, TC, L, NBUF, NWW
-            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 3, 4>(m, cg, a, mix, s);
-            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 4, 2>(m, cg, a, mix, s);
-            case 3: return launch_walk_t<Real, SW, 2, 16, 4, 2, 2>(m, cg, a, mix, s);
-            case 4: return launch_walk_t<Real, SW, 2, 16, 1, 6, 2>(m, cg, a, mix, s);
-            case 5: return launch_walk_t<Real, SW, 2, 8, 2, 3, 1>(m, cg, a, mix, s);
-            case 6: return launch_walk_t<Real, SW, 2, 8, 4, 3, 1>(m, cg, a, mix, s);
-            case 7: return launch_walk_t<Real, SW, 2, 16, 2, 2, 2>(m, cg, a, mix, s);
+        switch (variant) {   // NB, TC, L, NBUF, NI, NWW
+            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 3, 8, 2>(m, cg, a, mix, s);
+            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 2>(m, cg, a, mix, s);
+            case 3: return launch_walk_t<Real, SW, 2, 16, 2, 3, 2, 2>(m, cg, a, mix, s);
+            case 4: return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 2>(m, cg, a, mix, s);
+            case 5: return launch_walk_t<Real, SW, 2, 16, 2, 3, 4, 4>(m, cg, a, mix, s);
+            case 6: return launch_walk_t<Real, SW, 2, 8, 2, 3, 2, 1>(m, cg, a, mix, s);
+            case 7: return launch_walk_t<Real, SW, 2, 8, 2, 3, 4, 1>(m, cg, a, mix, s);
             default: break;
         }
 #endif
-        return launch_walk_t<Real, SW, 2, 16, 2, 3, 2>(m, cg, a, mix, s);
+        return launch_walk_t<Real, SW, 2, 16, 2, 3, 4, 2>(m, cg, a, mix, s);
     }
-    return launch_walk_t<Real, SW, 8, 8, 2, 3, 1>(m, cg, a, mix, s);
+    return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1>(m, cg, a, mix, s);
 }
 
 template <typename Real, bool SW>
