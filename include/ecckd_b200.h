@@ -122,6 +122,11 @@ int ecckd_model_load(const char *ckd_file, int ndev, const int *devices,
 
 void ecckd_model_destroy(ecckd_model *model);
 
+/* The loader alone (no device needed): load_and_init into host tables owned by the
+ * library -- inspect them, hand them to ecckd_model_create, then ecckd_tables_free. */
+int ecckd_tables_load(const char *ckd_file, const ecckd_host_tables **tables, char err[ECCKD_ERRLEN]);
+void ecckd_tables_free(const ecckd_host_tables *tables);
+
 /* ---- getters (gas_optics_ecckd.f90:477-553 + inherited get_ngpt/get_nband) - */
 int ecckd_get_ngas(const ecckd_model *model);
 int ecckd_get_gas_name(const ecckd_model *model, int i, char name[ECCKD_NAME_LEN]); /* 0-based */

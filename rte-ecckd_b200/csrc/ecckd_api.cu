@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -563,6 +565,41 @@ int ecckd_model_load(const char *ckd_file, int ndev, const int *devices, ecckd_m
 }
 
 void ecckd_model_destroy(ecckd_model *model) { delete model; }
+
+namespace {
+struct TablesHolder {
+    HostModel hm;
+    ecckd_host_tables view;
+};
+std::mutex g_tables_mutex;
+std::map<const ecckd_host_tables *, std::unique_ptr<TablesHolder>> g_tables;
+}  // namespace
+
+int ecckd_tables_load(const char *ckd_file, const ecckd_host_tables **tables, char err[ECCKD_ERRLEN])
+{
+    if (err) err[0] = '\0';
+    if (!ckd_file || !tables) { set_err(err, "ecckd_tables_load: NULL argument"); return ECCKD_ERR_ARG; }
+    *tables = nullptr;
+    try {
+        std::unique_ptr<TablesHolder> h(new TablesHolder);
+        h->hm = load_and_init(ckd_file);
+        h->view = h->hm.view();
+        const ecckd_host_tables *key = &h->view;
+        std::lock_guard<std::mutex> lock(g_tables_mutex);
+        g_tables[key] = std::move(h);
+        *tables = key;
+        return ECCKD_OK;
+    } catch (const std::exception &e) {
+        set_err(err, e.what());
+        return ECCKD_ERR_IO;
+    }
+}
+
+void ecckd_tables_free(const ecckd_host_tables *tables)
+{
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    g_tables.erase(tables);
+}
 
 int ecckd_get_ngas(const ecckd_model *m) { return m ? (int)m->gas.size() : 0; }                       // :477-483
 int ecckd_get_gas_name(const ecckd_model *m, int i, char name[ECCKD_NAME_LEN])                         // :507-513

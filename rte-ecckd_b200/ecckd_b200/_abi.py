@@ -48,6 +48,8 @@ _SIGS = {
     "ecckd_model_create": (_i, [C.POINTER(HostTables), _i, C.POINTER(C.c_int), C.POINTER(_vp), _cp]),
     "ecckd_model_load": (_i, [_cp, _i, C.POINTER(C.c_int), C.POINTER(_vp), _cp]),
     "ecckd_model_destroy": (None, [_vp]),
+    "ecckd_tables_load": (_i, [_cp, C.POINTER(C.POINTER(HostTables)), _cp]),
+    "ecckd_tables_free": (None, [C.POINTER(HostTables)]),
     "ecckd_get_ngas": (_i, [_vp]),
     "ecckd_get_gas_name": (_i, [_vp, _i, _cp]),
     "ecckd_get_ngpt": (_i, [_vp]),

@@ -1,0 +1,337 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): interpolation indices bit-exact; fp64 tau/ssa/g/sources within 1e-12
+relative; the fp32 variant within 1e-5 relative (vs the fp64 oracle on the fp32-rounded inputs).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ecckd_b200
+from ecckd_b200 import synthetic
+from conftest import FILES, atm_numpy, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
+KERNELS = {"walk": ecckd_b200.KERNEL_WALK, "generic": ecckd_b200.KERNEL_GENERIC}
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gpu_models(dev):
+    return {k: ecckd_b200.GasOpticsEcckd.load(v) for k, v in FILES.items()}
+
+
+def to_dev(a, dtype, dev):
+    return ecckd_b200.to_fortran(torch.as_tensor(np.ascontiguousarray(a)), dtype, dev)
+
+
+def run_gpu(go, plev, tlay, tlev, tsfc, gases, dtype, dev, kernel=ecckd_b200.KERNEL_AUTO, **kw):
+    """numpy inputs -> device call -> numpy outputs"""
+    lw = go.source_is_internal()
+    gl = [(n, to_dev(v, dtype, dev) if isinstance(v, np.ndarray) else v) for n, v in gases]
+    out = go.gas_optics(None, to_dev(plev, dtype, dev), to_dev(tlay, dtype, dev),
+                        torch.as_tensor(tsfc).to(dev, dtype) if lw else None, gl,
+                        tlev=to_dev(tlev, dtype, dev) if (lw and tlev is not None) else None, kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def run_oracle(co, m, plev, tlay, tlev, tsfc, gases, dtype=torch.float64):
+    if dtype == torch.float32:   # the fp32 variant sees fp32-rounded inputs
+        r = lambda a: np.asfortranarray(np.asarray(a, dtype=np.float32).astype(np.float64))
+        plev, tlay, tlev, tsfc = r(plev), r(tlay), r(tlev), r(tsfc)
+        gases = [(n, r(v) if isinstance(v, np.ndarray) else float(np.float32(v))) for n, v in gases]
+    out, err = co.gas_optics_ext(plev, tlay, gases) if m.shortwave else co.gas_optics_int(plev, tlay, tsfc, gases, tlev)
+    assert err == ""
+    return out
+
+
+def check(out, ref, tol, what=""):
+    for k, v in ref.items():
+        e = rel_err(out[k], v)
+        assert e <= tol, f"{what} {k}: rel err {e:.3e} > {tol}"
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("key", list(FILES))
+def test_gcm_block_parity(key, kernel, dtype, dev, gpu_models, ck_models, c_oracles):
+    """137-layer GCM-like columns (config 4 at oracle-sized ncol; 70 columns = 4 full tiles + a ragged one)."""
+    inp = atm_numpy(synthetic.make_atmosphere(70, 137))
+    out = run_gpu(gpu_models[key], *inp, dtype, dev, KERNELS[kernel])
+    check(out, run_oracle(c_oracles[key], ck_models[key], *inp, dtype), TOL[dtype], f"{key}/{kernel}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("key", list(FILES))
+def test_rfmip_shaped_parity(key, dtype, dev, gpu_models, ck_models, c_oracles):
+    """Configs 1-3: 18 experiments x 100 columns x 60 layers, scalar gases straddling the ch4/n2o references."""
+    for e, atm in enumerate(synthetic.make_rfmip_like()):
+        inp = atm_numpy(atm)
+        out = run_gpu(gpu_models[key], *inp, dtype, dev)
+        check(out, run_oracle(c_oracles[key], ck_models[key], *inp, dtype), TOL[dtype], f"{key}/exp{e}")
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("key", list(FILES))
+def test_committed_golden_fixtures(key, kernel, dev, gpu_models):
+    """GPU vs tests/golden (hand-built columns hitting every clamp / branch)."""
+    z = np.load(os.path.join(GOLD, "inputs.npz"))
+    f = np.asfortranarray
+    gases = [("co2", 420e-6), ("ch4", 1.0e-6), ("n2o", 4.0e-7), ("o2", 0.209), ("cfc11", 2.3e-10),
+             ("cfc12", 5.2e-10), ("h2o", f(z["h2o"])), ("o3", f(z["o3"])), ("no2", 0.0)]
+    out = run_gpu(gpu_models[key], f(z["plev"]), f(z["tlay"]), f(z["tlev"]), z["tsfc"], gases, torch.float64, dev, KERNELS[kernel])
+    gold = np.load(os.path.join(GOLD, f"{key}.npz"))
+    check(out, {k: gold[k] for k in out}, 1e-12, f"golden {key}/{kernel}")
+
+
+@pytest.mark.parametrize("key", list(FILES))
+def test_indices_are_bit_exact(key, dev, gpu_models, c_oracles):
+    """ip0 / it0 / iv0 as the kernels compute them == the oracle's, exactly; weights to the last bits
+    (the only non-IEEE step is log(): CUDA's vs libm's, both < 1 ulp)."""
+    atms = [synthetic.make_atmosphere(257, 137)] + synthetic.make_rfmip_like(nexp=3)
+    z = np.load(os.path.join(GOLD, "inputs.npz"))
+    cases = [atm_numpy(a) for a in atms]
+    cases.append((np.asfortranarray(z["plev"]), np.asfortranarray(z["tlay"]), None, None, [("h2o", np.asfortranarray(z["h2o"]))]))
+    for plev, tlay, _, _, gl in cases:
+        h2o = dict(gl)["h2o"]
+        ref = c_oracles[key].indices("h2o", plev, tlay, h2o)
+        got = gpu_models[key].interpolation_indices(to_dev(plev, torch.float64, dev), to_dev(tlay, torch.float64, dev),
+                                                    "h2o", to_dev(h2o, torch.float64, dev))
+        got = {k: v.cpu().numpy() for k, v in got.items()}
+        for k in ("ip0", "it0", "iv0"):
+            bad = np.argwhere(got[k] != ref[k])
+            msg = ""
+            if bad.size:   # would only happen when the index variable sits within an ulp of an integer
+                i, j = bad[0]
+                msg = f"{k} differs at {tuple(bad[0])}: gpu {got[k][i, j]} oracle {ref[k][i, j]} weights {got[k.replace('i', '', 1)[0] + 'w1'][i, j] if False else ''}"
+            assert not bad.size, msg
+        for k in ("pw1", "tw1", "vw1"):
+            assert np.max(np.abs(got[k] - ref[k])) <= 2e-13, k
+
+
+def test_planck_indices_bit_exact(dev, gpu_models, c_oracles):
+    T = np.concatenate([np.linspace(90, 420, 4001), [120.0, 119.99999999, 350.0, 350.00000001, 121.0]])
+    it_ref, w_ref = c_oracles["lw_fsck"].planck_indices(T)
+    it, w = gpu_models["lw_fsck"].planck_indices(torch.as_tensor(T).to(dev))
+    assert np.array_equal(it.cpu().numpy(), it_ref[:, 0])
+    assert np.array_equal(w.cpu().numpy(), w_ref[:, 0])        # pure IEEE arithmetic: identical
+
+
+# ---- shapes: empty, single, ragged ----------------------------------------------------------------
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("ncol,nlay", [(1, 1), (1, 137), (17, 33), (16, 32), (15, 31), (33, 64), (3, 65)])
+def test_ragged_shapes(ncol, nlay, kernel, dev, gpu_models, ck_models, c_oracles):
+    for key in ("lw_rrtmgp", "sw_wide"):      # 36 g-points = two g-groups, 27 = a partial one
+        inp = atm_numpy(synthetic.make_atmosphere(ncol, nlay, col0=1000))
+        out = run_gpu(gpu_models[key], *inp, torch.float64, dev, KERNELS[kernel])
+        check(out, run_oracle(c_oracles[key], ck_models[key], *inp), 1e-12, f"{key} {ncol}x{nlay}")
+
+
+def test_empty_call_is_a_no_op(dev, gpu_models):
+    go = gpu_models["lw_fsck"]
+    z2 = lambda n: ecckd_b200.fortran_empty((0, n), torch.float64, dev)
+    out = go.gas_optics(None, z2(11), z2(10), torch.empty(0, dtype=torch.float64, device=dev), [("co2", 4e-4)], tlev=z2(11))
+    assert out["tau"].shape == (0, 10, 32)
+
+
+# ---- gas handling (gas_optical_depth :323-376) ----------------------------------------------------
+def _small():
+    return atm_numpy(synthetic.make_atmosphere(40, 60, col0=77))
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_gas_list_semantics(kernel, dev, gpu_models, ck_models, c_oracles):
+    plev, tlay, tlev, tsfc, gases = _small()
+    g = dict(gases)
+    variants = {
+        "unknown gases skipped": gases + [("sf6", 1e-9), ("co", 1e-7)],
+        "reordered": list(reversed(gases)),
+        "no o3": [x for x in gases if x[0] != "o3"],
+        "composite via n2 only": [x for x in gases if x[0] != "o2"] + [("n2", 0.781)],
+        "composite twice (o2 then n2)": gases + [("n2", 0.781)],
+        "no composite": [x for x in gases if x[0] != "o2"],
+        "nothing": [],
+        "only h2o": [("h2o", g["h2o"])],
+        "ch4/n2o below reference": [(n, (1e-7 if n in ("ch4", "n2o") else v)) for n, v in gases],
+        "profiles": [(n, (np.linspace(1, 2, tlay.shape[1]) * v if n in ("co2", "cfc11") else v)) for n, v in gases],
+        "all fields": [(n, v if isinstance(v, np.ndarray) else np.asfortranarray(v * (1 + 0.2 * np.cos(np.arange(tlay.size)).reshape(tlay.shape)))) for n, v in gases],
+        "zero concentrations": [(n, (0.0 if not isinstance(v, np.ndarray) else v * 0)) for n, v in gases],
+    }
+    for key in ("lw_fsck", "sw_wide"):
+        for name, gl in variants.items():
+            out = run_gpu(gpu_models[key], plev, tlay, tlev, tsfc, gl, torch.float64, dev, KERNELS[kernel])
+            check(out, run_oracle(c_oracles[key], ck_models[key], plev, tlay, tlev, tsfc, gl), 1e-12, f"{key}/{kernel}/{name}")
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_surface_first_ordering(kernel, dev, gpu_models, ck_models, c_oracles):
+    """Q6: upside-down columns.  Gas weights go negative -> clamped to zero, except relative_linear gases
+    below their reference (negative x negative), which the reference keeps; Rayleigh goes negative unclamped."""
+    plev, tlay, tlev, tsfc, gases = _small()
+    f = np.asfortranarray
+    flip = lambda a: f(a[:, ::-1])
+    gl = [(n, flip(v) if isinstance(v, np.ndarray) else v) for n, v in gases]
+    gl = [(n, (1e-7 if n == "ch4" else v)) for n, v in gl]      # ch4 below reference: contributes when dp < 0
+    for key in ("lw_fsck", "sw_wide"):
+        out = run_gpu(gpu_models[key], flip(plev), flip(tlay), flip(tlev), tsfc, gl, torch.float64, dev, KERNELS[kernel])
+        ref = run_oracle(c_oracles[key], ck_models[key], flip(plev), flip(tlay), flip(tlev), tsfc, gl)
+        check(out, ref, 1e-12, f"{key}/{kernel}/upside-down")
+        if key == "lw_fsck":
+            assert (ref["tau"] > 0).any()       # the ch4 term survived the clamp
+
+
+# ---- reference error behaviour --------------------------------------------------------------------
+def test_missing_tlev_error_after_partial_write(dev, gpu_models, ck_models, c_oracles):
+    plev, tlay, tlev, tsfc, gases = _small()
+    with pytest.raises(ecckd_b200.EcckdError) as ei:
+        run_gpu(gpu_models["lw_fsck"], plev, tlay, None, tsfc, gases, torch.float64, dev)
+    assert ei.value.code == ecckd_b200.ERR_REFERENCE and str(ei.value) == "tlev is required for ecckd"   # :414-417
+    ref = run_oracle(c_oracles["lw_fsck"], ck_models["lw_fsck"], plev, tlay, tlev, tsfc, gases)
+    part = {k: v.cpu().numpy() for k, v in ei.value.partial.items()}
+    check(part, {k: ref[k] for k in ("tau", "lay_source", "sfc_source")}, 1e-12, "partial")
+
+
+def test_sw_needs_two_stream(dev, gpu_models, ck_models, c_oracles):
+    plev, tlay, tlev, tsfc, gases = _small()
+    with pytest.raises(ecckd_b200.EcckdError) as ei:
+        run_gpu(gpu_models["sw_wide"], plev, tlay, None, None, gases, torch.float64, dev, two_stream=False)
+    assert ei.value.code == ecckd_b200.ERR_REFERENCE and str(ei.value) == "shortwave must use ty_optical_props_2str"   # :461-463
+    ref = run_oracle(c_oracles["sw_wide"], ck_models["sw_wide"], plev, tlay, tlev, tsfc, gases)
+    check({"tau": ei.value.partial["tau"].cpu().numpy()}, {"tau": ref["tau"]}, 1e-12, "1scl tau")
+
+
+def test_wrong_band_and_bad_arguments(dev, gpu_models):
+    plev, tlay, tlev, tsfc, gases = _small()
+    with pytest.raises(ecckd_b200.EcckdError) as ei:       # LW call on SW tables
+        run_gpu(gpu_models["sw_wide"], plev, tlay, tlev, tsfc, gases, torch.float64, dev) if False else \
+            gpu_models["sw_wide"].gas_optics(None, to_dev(plev, torch.float64, dev), to_dev(tlay, torch.float64, dev),
+                                             torch.as_tensor(tsfc).to(dev), [], tlev=to_dev(tlev, torch.float64, dev))
+    assert ei.value.code == ecckd_b200.ERR_ARG
+    with pytest.raises(ValueError):                         # row-major array refused
+        gpu_models["lw_fsck"].gas_optics(None, torch.zeros(40, 61, dtype=torch.float64, device=dev), to_dev(tlay, torch.float64, dev),
+                                         torch.as_tensor(tsfc).to(dev), [], tlev=to_dev(tlev, torch.float64, dev))
+
+
+def test_getters(gpu_models, ck_models):
+    for key, go in gpu_models.items():
+        m = ck_models[key]
+        assert go.get_ngas() == m.num_gases and go.get_gases() == m.gas and go.get_ngpt() == m.ngpt
+        assert go.source_is_internal() == (not m.shortwave) and go.source_is_external() == m.shortwave
+        assert go.get_press_min() == np.exp(m.log_pressure[0]) and go.get_press_max() == np.exp(m.log_pressure[-1])   # :517-533
+        assert go.get_temp_min() == m.temperature.min() and go.get_temp_max() == m.temperature.max()                 # :537-553
+        assert np.array_equal(go.get_band2gpt().T, m.band2gpt) and go.get_nband() == m.band2gpt.shape[0]
+    assert abs(gpu_models["sw_wide"].get_total_solar_irradiance() - ck_models["sw_wide"].total_solar_irradiance) < 1e-9
+    assert abs(gpu_models["lw_fsck"].get_press_min() - 0.6940532) < 1e-6
+
+
+# ---- host-array path (what the plain Fortran shim calls) --------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("block_cols", [0, 7, 64])
+def test_host_path_equals_device_path(block_cols, dtype, dev, gpu_models):
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    plev, tlay, tlev, tsfc, gases = atm_numpy(synthetic.make_atmosphere(50, 60, col0=5))
+    c = lambda a: np.asfortranarray(np.asarray(a, dtype=dtype))
+    gl = [(n, c(v) if isinstance(v, np.ndarray) else v) for n, v in gases] + [("cfc11", 1e-10 * np.ones(60))]
+    for key in ("lw_fsck", "sw_wide"):
+        go = gpu_models[key]
+        lw = go.source_is_internal()
+        host = go.gas_optics(None, c(plev), c(tlay), c(tsfc) if lw else None, gl, tlev=c(tlev) if lw else None, block_cols=block_cols)
+        devo = run_gpu(go, c(plev), c(tlay), c(tlev), c(tsfc), gl, tdt, dev)
+        for k in devo:
+            assert np.array_equal(host[k], devo[k]), f"{key} {k}"      # same kernel, same per-column arithmetic: bitwise
+
+
+def test_host_path_error_paths(dev, gpu_models):
+    plev, tlay, tlev, tsfc, gases = _small()
+    with pytest.raises(ecckd_b200.EcckdError) as ei:
+        gpu_models["lw_fsck"].gas_optics(None, plev, tlay, tsfc, gases, tlev=None)
+    assert str(ei.value) == "tlev is required for ecckd" and np.isfinite(ei.value.partial["tau"]).all()
+
+
+# ---- sharding and size-independent properties -------------------------------------------------------
+def test_column_shards_reproduce_the_unsharded_result_bitwise(dev, gpu_models):
+    """SURVEY 8e determinism check: any column split gives bit-identical outputs (no cross-column coupling)."""
+    from ecckd_b200 import sharding
+    plev, tlay, tlev, tsfc, gases = atm_numpy(synthetic.make_atmosphere(203, 137))
+    for key in ("lw_fsck", "sw_wide"):
+        full = run_gpu(gpu_models[key], plev, tlay, tlev, tsfc, gases, torch.float64, dev)
+        for world in (2, 8):
+            parts = []
+            for r in range(world):
+                c0, c1 = sharding.shard_columns(203, world, r)
+                f = np.asfortranarray
+                gl = [(n, f(v[c0:c1]) if isinstance(v, np.ndarray) else v) for n, v in gases]
+                parts.append(run_gpu(gpu_models[key], f(plev[c0:c1]), f(tlay[c0:c1]), f(tlev[c0:c1]), tsfc[c0:c1], gl, torch.float64, dev))
+            for k in full:
+                assert np.array_equal(np.concatenate([p[k] for p in parts], 0), full[k]), f"{key} {k} world={world}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_large_block_properties(dtype, dev, gpu_models, ck_models, c_oracles):
+    """A 32768-column x 137-layer block generated on the device (the bench's generator and block shape class):
+    size-independent properties plus oracle parity on sampled columns and walk-vs-generic agreement."""
+    ncol, nlay = 32768, 137
+    atm = synthetic.make_atmosphere(ncol, nlay, device=dev)
+    if dtype == torch.float32:
+        atm = atm.astype(dtype)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    pick = torch.tensor([0, 1, 15, 16, 17, 4095, 20000, ncol - 1], device=dev)
+    for key in ("lw_fsck", "sw_wide"):
+        go, m = gpu_models[key], ck_models[key]
+        lw = not m.shortwave
+        gases = ecckd_b200.PreparedGases(atm.gas_list(), ncol, nlay, npdt, dev)
+        call = lambda kern: go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc if lw else None, gases,
+                                          tlev=atm.tlev if lw else None, kernel=kern)
+        out = call(ecckd_b200.KERNEL_WALK)
+        gen = call(ecckd_b200.KERNEL_GENERIC)
+        torch.cuda.synchronize()
+        for k in out:                                                     # two independent CUDA formulations agree
+            a, b = out[k].double(), gen[k].double()
+            e = ((a - b).abs() / b.abs().clamp_min(1e-300)).max().item() if a.numel() else 0.0
+            assert e <= (1e-12 if dtype == torch.float64 else 2e-5), f"{key} {k}: walk vs generic {e:.3e}"
+        assert torch.isfinite(out["tau"]).all() and (out["tau"] > 0).all()
+        if lw:
+            # the level source is computed once and written twice (:423-424): inc(:, j) == dec(:, j+1), bitwise
+            assert torch.equal(out["lev_source_inc"][:, :-1, :], out["lev_source_dec"][:, 1:, :])
+            assert (out["lay_source"] > 0).all() and (out["sfc_source"] > 0).all()
+        else:
+            assert (out["g"] == 0).all() and ((out["ssa"] > 0) & (out["ssa"] < 1)).all()
+            sol = torch.as_tensor(m.solar_irradiance, device=dev).to(dtype)
+            assert torch.equal(out["toa_src"], sol[None, :].expand(ncol, -1))
+        # oracle parity on sampled columns of exactly these device-generated inputs
+        sel = lambda t: np.asfortranarray(t[pick].double().cpu().numpy())
+        gl = [(n, sel(v) if torch.is_tensor(v) else (float(np.float32(v)) if dtype == torch.float32 else v)) for n, v in atm.gas_list()]
+        ref = run_oracle(c_oracles[key], m, sel(atm.plev), sel(atm.tlay), sel(atm.tlev), atm.tsfc[pick].double().cpu().numpy(), gl)
+        check({k: v[pick].cpu().numpy() for k, v in out.items()}, ref, TOL[dtype], f"{key} sampled")
+        # permuting the columns permutes the outputs, bitwise (columns are independent)
+        perm = torch.randperm(4096, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        sub = lambda t: ecckd_b200.to_fortran(t[:4096][perm], dtype, dev)
+        gl2 = [(n, sub(v) if torch.is_tensor(v) else v) for n, v in atm.gas_list()]
+        o2 = go.gas_optics(None, sub(atm.plev), sub(atm.tlay), atm.tsfc[:4096][perm].contiguous() if lw else None, gl2,
+                           tlev=sub(atm.tlev) if lw else None)
+        assert torch.equal(o2["tau"], out["tau"][:4096][perm])
+
+
+def test_linearity_in_a_linear_gas(dev, gpu_models):
+    """tau is affine in the concentration of a code-1 gas: tau(2x) - tau(x) == tau(x) - tau(0) to rounding."""
+    plev, tlay, tlev, tsfc, gases = _small()
+    base = dict(gases)
+    def tau(scale):
+        gl = [(n, (v * scale if n == "o3" else v)) for n, v in gases]
+        return run_gpu(gpu_models["lw_fsck"], plev, tlay, tlev, tsfc, gl, torch.float64, dev)["tau"]
+    t0, t1, t2 = tau(0.0), tau(1.0), tau(2.0)
+    d1, d2 = t1 - t0, t2 - t1
+    assert np.max(np.abs(d2 - d1) / np.maximum(t2, 1e-300)) <= 1e-13
