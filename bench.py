@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- LW+SW ECCKD gas-optics throughput (g-point-layers/s) on B200, with the HBM roofline
+fraction of the dominant kernel and the CPU restatement of the reference timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over the workload: longwave (ecckd-1.2 fsck-tol0.0161, 32 g-points:
+tau + Planck lay/lev/sfc sources) plus shortwave (wide-tol0.05, 27 g-points: tau/ssa/g + Rayleigh + TOA
+source) gas optics of a synthetic GCM block of --cols columns x 137 layers per GPU (BASELINE.json
+configs[3]: 1M columns on one B200; N GPUs = N x 1M columns, column-sharded, no collective).  Inputs are
+resident in HBM when the timed region starts; outputs (140 + 89 GB per 1M columns in fp64, more than HBM)
+go through a ring of two column-block output buffers, as a host model consumes them block by block.
+
+`value`  : whole-job g-point-layers/s, device-resident arrays, CUDA events, max over ranks.
+`e2e`    : the same rate through the host-array C-ABI entry points (ecckd_gas_optics_{lw,sw}_host_f64):
+           pinned host inputs -> H2D -> kernels -> D2H of every output, all inside the timed region.
+`roofline`: LW walking kernel, algorithmic bytes / CUDA-event duration vs the measured HBM copy bandwidth.
+`cpu_baseline` / --impl reference: oracle/ecckd_oracle.c (-O3 -march=native, all host threads) -- a port:
+           the Fortran reference cannot be built offline (no Fortran compiler, netCDF-Fortran, rte-rrtmgp).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "rte-ecckd_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+DATA = os.path.join(ROOT, "data")
+LW_FILE = os.path.join(DATA, "ecckd-1.2_lw_ckd-definition_climate_fsck-tol0.0161.nc")
+SW_FILE = os.path.join(DATA, "ecckd-1.2_sw_ckd-definition_climate_wide-tol0.05.nc")
+NLAY = 137
+NG_LW, NG_SW = 32, 27
+METRIC = "LW+SW gas-optics g-point-layers/s"
+UNIT = "g-point-layers/s"
+
+
+def algorithmic_bytes(ncol: int, nlay: int, ngpt: int, lw: bool, w: int = 8) -> int:
+    """inputs read + optical properties and sources written (2 two-dimensional gases)."""
+    if lw:
+        return w * ncol * (2 * (nlay + 1) + 3 * nlay + 1) + w * ncol * (4 * nlay * ngpt + ngpt)
+    return w * ncol * ((nlay + 1) + 3 * nlay) + w * ncol * (3 * nlay * ngpt + ngpt)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (device copy, measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per LW launch from the committed ncu capture, scaled per column."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+_REBUILT = False
+
+
+def cpu_port_rate(ncol: int, threads: int, block: int = 16, reps: int = 1):
+    """Time the oracle's -O3 -march=native build on `ncol` synthetic columns (LW + SW), blocks of `block`
+    columns handed to `threads` POSIX threads (the reference driver's loop over independent column blocks).
+    Returns (g-point-layers/s, seconds, threads)."""
+    import torch
+    from ecckd_b200 import synthetic
+    from oracle import ckd_model
+    from oracle.c_oracle import COracle, load
+
+    global _REBUILT
+    if not _REBUILT:
+        load(fast=True, rebuild=True)      # -march=native must match THIS host, not the box the repo was built on
+        _REBUILT = True
+    atm = synthetic.make_atmosphere(ncol, NLAY)
+    nblocks = ncol // block
+    ncol = nblocks * block
+
+    def blocked(t, n2):   # (ncol, n2) column-major -> (nblocks, n2, block) C order == Fortran (block, n2, nblocks)
+        a = t.numpy()[:ncol]
+        return np.ascontiguousarray(a.reshape(nblocks, block, n2).transpose(0, 2, 1))
+
+    plev, tlay, tlev = blocked(atm.plev, NLAY + 1), blocked(atm.tlay, NLAY), blocked(atm.tlev, NLAY + 1)
+    tsfc = np.ascontiguousarray(atm.tsfc.numpy()[:ncol])
+    gases = [(n, blocked(v, NLAY) if torch.is_tensor(v) else v) for n, v in atm.gas_list()]
+    lw = COracle(ckd_model.load_and_init(LW_FILE), fast=True)
+    sw = COracle(ckd_model.load_and_init(SW_FILE), fast=True)
+    if threads <= 0:
+        threads = lw.max_threads()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lw.run_blocks(True, block, NLAY, nblocks, plev, tlay, tsfc, tlev, gases, threads)
+        sw.run_blocks(False, block, NLAY, nblocks, plev, tlay, None, None, gases, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return ncol * NLAY * (NG_LW + NG_SW) / best, best, threads
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """--impl reference: the reference's CPU path (port) on the box's host cores, same metric / config."""
+    if rank != 0:
+        return
+    ncol = args.ref_cols
+    for _ in range(args.warmup):
+        cpu_port_rate(min(ncol, 2048), 0)
+    times, threads = [], 0
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        rate, dt, threads = cpu_port_rate(ncol, 0)
+        times.append(dt)
+    total = time.perf_counter() - t_all
+    ms = 1e3 * sum(times) / len(times)
+    value = ncol * NLAY * (NG_LW + NG_SW) / (ms * 1e-3)
+    sample = f"{ncol} synthetic columns x {NLAY} layers per step (LW 32 + SW 27 g-points), blocks of 16 columns over {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic GCM block, columns x 137 layers, LW+SW (bounded sample of BASELINE.json configs[3])",
+                   "columns_per_step": ncol, "nlay": NLAY, "ngpt_lw": NG_LW, "ngpt_sw": NG_SW,
+                   "note": "CPU restatement (oracle/ecckd_oracle.c, -O3 -march=native) of src/gas_optics_ecckd.f90; the Fortran "
+                           "reference itself cannot be built offline (no Fortran compiler / netCDF-Fortran / rte-rrtmgp)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cols", type=int, default=1 << 20, help="columns per GPU per step (BASELINE configs[3]: 1M)")
+    ap.add_argument("--block", type=int, default=1 << 16, help="columns per kernel launch / output ring slot")
+    ap.add_argument("--e2e-cols", type=int, default=1 << 17, help="columns per GPU per e2e step (host-array path)")
+    ap.add_argument("--e2e-block", type=int, default=1 << 14)
+    ap.add_argument("--cpu-cols", type=int, default=1 << 15, help="bounded sample for cpu_baseline")
+    ap.add_argument("--ref-cols", type=int, default=1 << 15, help="columns per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ecckd_b200
+    from ecckd_b200 import sharding, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices: the product path has no CPU fallback")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    ncol, B = args.cols, min(args.block, args.cols)
+    nblk = (ncol + B - 1) // B
+    col_base = rank * ncol                      # weak scaling: every GPU owns its own `cols` columns of the global grid
+    lw = ecckd_b200.GasOpticsEcckd.load(LW_FILE, devices=[local_rank])
+    sw = ecckd_b200.GasOpticsEcckd.load(SW_FILE, devices=[local_rank])
+
+    # ---- inputs resident in HBM, already blocked like the reference driver blocks them -------------
+    blocks = []
+    for b in range(nblk):
+        nb = min(B, ncol - b * B)
+        atm = synthetic.make_atmosphere(nb, NLAY, col0=col_base + b * B, device=dev)
+        blocks.append((atm, ecckd_b200.PreparedGases(atm.gas_list(), nb, NLAY, np.float64, dev)))
+    FE = ecckd_b200.fortran_empty
+    ring = [{"lw": {k: FE((B, NLAY, NG_LW), torch.float64, dev) for k in ("tau", "lay_source", "lev_source_inc", "lev_source_dec")},
+             "sw": {k: FE((B, NLAY, NG_SW), torch.float64, dev) for k in ("tau", "ssa", "g")}} for _ in range(2)]
+    for r in ring:
+        r["lw"]["sfc_source"] = FE((B, NG_LW), torch.float64, dev)
+        r["sw"]["toa_src"] = FE((B, NG_SW), torch.float64, dev)
+
+    def outs(slot, band, nb):
+        o = ring[slot][band]
+        return o if nb == B else {k: FE(tuple([nb] + list(v.shape[1:])), torch.float64, dev) for k, v in o.items()}
+
+    ev_pairs = {"lw": [], "sw": []}
+
+    def step(timed: bool):
+        for b, (atm, gases) in enumerate(blocks):
+            slot = b & 1
+            if timed:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record()
+            lw.gas_optics(None, atm.plev, atm.tlay, atm.tsfc, gases, tlev=atm.tlev, out=outs(slot, "lw", atm.ncol))
+            if timed:
+                e[1].record()
+            sw.gas_optics(None, atm.plev, atm.tlay, None, gases, out=outs(slot, "sw", atm.ncol))
+            if timed:
+                e[2].record()
+                ev_pairs["lw"].append((e[0], e[1], atm.ncol)); ev_pairs["sw"].append((e[1], e[2], atm.ncol))
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    sharding.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.steps):
+        step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_step = sharding.max_over_ranks(t0.elapsed_time(t1) / args.steps, dev)
+    gptl_step = ncol * NLAY * (NG_LW + NG_SW) * world
+    value = gptl_step / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (LW walk): live CUDA-event durations of every timed launch -
+    peak, peak_src = measured_peak()
+    full = [(a.elapsed_time(bb), n) for a, bb, n in ev_pairs["lw"] if n == B]
+    lw_ms = statistics.mean(t for t, _ in full) if full else float("nan")
+    bytes_lw = algorithmic_bytes(B, NLAY, NG_LW, True)
+    achieved = bytes_lw / (lw_ms * 1e-3) / 1e9
+    traffic = profiled_traffic()
+    roofline = {"bound": "hbm", "kernel": "ecckd::walk_kernel<double, LW> (+ per-call table-mix kernel, <1% of the time)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (traffic["lw_dram_bytes_per_column"] * B if traffic else None),
+                "algorithmic_bytes_per_launch": bytes_lw, "columns_per_launch": B, "ms_per_launch": lw_ms, "peak_source": peak_src}
+    fsw = [(a.elapsed_time(bb), n) for a, bb, n in ev_pairs["sw"] if n == B]
+    sw_ms = statistics.mean(t for t, _ in fsw) if fsw else float("nan")
+    bytes_sw = algorithmic_bytes(B, NLAY, NG_SW, False)
+    roofline_sw = {"bound": "hbm", "kernel": "ecckd::walk_kernel<double, SW>", "achieved": bytes_sw / (sw_ms * 1e-3) / 1e9, "peak": peak,
+                   "unit": "GB/s", "frac": bytes_sw / (sw_ms * 1e-3) / 1e9 / peak, "traffic": (traffic["sw_dram_bytes_per_column"] * B if traffic else None),
+                   "ms_per_launch": sw_ms}
+    launches = args.steps * nblk * 4          # per block: LW mix + LW walk + SW mix + SW walk
+
+    # free the device-resident workload before the host-array measurement
+    del blocks, ring
+    torch.cuda.empty_cache()
+
+    # ---- e2e: host arrays through the C ABI's host entry points ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ne, EB = min(args.e2e_cols, ncol), min(args.e2e_block, args.e2e_cols)
+        nhb = (ne + EB - 1) // EB
+        pin = lambda t: t.cpu().pin_memory()
+        hblocks = []
+        for b in range(nhb):
+            nb = min(EB, ne - b * EB)
+            atm = synthetic.make_atmosphere(nb, NLAY, col0=col_base + b * EB, device=dev)
+            # pinned host copies; numpy views of them are what a host model would hand to the shim
+            h = {k: pin(getattr(atm, k).t().contiguous()).numpy().T for k in ("plev", "tlay", "tlev", "h2o", "o3")}
+            h["tsfc"] = pin(atm.tsfc).numpy()
+            gl = [(n, (h[n] if n in ("h2o", "o3") else v)) for n, v in atm.gas_list()]
+            hblocks.append((nb, h, ecckd_b200.PreparedGases(gl, nb, NLAY, np.float64, None)))
+        hp = lambda shape: torch.empty(shape[::-1], dtype=torch.float64).pin_memory().numpy().T
+        hout = {"lw": {k: hp((EB, NLAY, NG_LW)) for k in ("tau", "lay_source", "lev_source_inc", "lev_source_dec")},
+                "sw": {k: hp((EB, NLAY, NG_SW)) for k in ("tau", "ssa", "g")}}
+        hout["lw"]["sfc_source"] = hp((EB, NG_LW)); hout["sw"]["toa_src"] = hp((EB, NG_SW))
+        h2d = d2h = 0
+        for nb, h, _ in hblocks:
+            h2d += 8 * nb * (2 * (NLAY + 1) + 3 * NLAY + 1) + 8 * nb * ((NLAY + 1) + 3 * NLAY) + 8 * 2 * 7
+            d2h += 8 * nb * (4 * NLAY * NG_LW + NG_LW) + 8 * nb * (3 * NLAY * NG_SW + NG_SW)
+
+        def e2e_step():
+            for nb, h, gases in hblocks:
+                ol = hout["lw"] if nb == EB else None
+                osw = hout["sw"] if nb == EB else None
+                lw.gas_optics(None, h["plev"], h["tlay"], h["tsfc"], gases, tlev=h["tlev"], out=ol, block_cols=EB // 2)
+                sw.gas_optics(None, h["plev"], h["tlay"], None, gases, out=osw, block_cols=EB // 2)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        k_e2e = max(2, min(args.steps, 5))
+        w0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()                       # host entry points are synchronous: results are in host memory on return
+        torch.cuda.synchronize()
+        dt = sharding.max_over_ranks((time.perf_counter() - w0) / k_e2e, dev)
+        sharding.barrier()
+        e2e = {"value": ne * NLAY * (NG_LW + NG_SW) * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "columns_per_step": ne, "block_cols": EB, "ms_per_step": dt * 1e3,
+               "api": "ecckd_gas_optics_{lw,sw}_host_f64 (pinned host arrays, H2D + kernels + D2H per column block)",
+               "pcie_d2h_GBps": d2h / dt / 1e9}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, secs, threads = cpu_port_rate(args.cpu_cols, 0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_cols} of the same synthetic columns x {NLAY} layers, LW+SW, {secs:.1f} s on {threads} threads "
+                         "(oracle/ecckd_oracle.c -O3 -march=native; Fortran reference not buildable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic GCM block, 1M columns x 137 layers, LW+SW on 1 B200, fp64 (BASELINE.json configs[3]); "
+                                   "N GPUs = N x 1M columns column-sharded, no collective",
+                       "columns_per_gpu": ncol, "nlay": NLAY, "ngpt_lw": NG_LW, "ngpt_sw": NG_SW, "columns_per_launch": B,
+                       "ck_definitions": [os.path.basename(LW_FILE), os.path.basename(SW_FILE)],
+                       "l2": "every launch streams >9 GB of outputs and 0.36 GB of inputs: far larger than the 126 MB L2, no flush needed",
+                       "gases": "h2o, o3 (ncol,nlay) fields; co2, ch4, n2o, o2, cfc11, cfc12 scalars (RFMIP convention)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_sw": roofline_sw,
+            "cpu_baseline": cpu,
+            "split": {"lw_gptl_per_s_per_gpu": B * NLAY * NG_LW / (lw_ms * 1e-3), "sw_gptl_per_s_per_gpu": B * NLAY * NG_SW / (sw_ms * 1e-3)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,10 +73,15 @@ def to_fortran(a, dtype=None, device=None):
     return out
 
 
+_EMPTY = C.create_string_buffer(16)   # stands in for the (never dereferenced) address of a zero-size array
+
+
 def _ptr(a, shape, np_dtype, what: str) -> int:
     """Address of a column-major array after checking shape / dtype / layout."""
     if a is None:
         return 0
+    if int(np.prod(tuple(a.shape))) == 0 and tuple(a.shape) == tuple(int(s) for s in shape):
+        return C.addressof(_EMPTY)        # present but empty: must not look like an absent optional argument
     shape = tuple(int(s) for s in shape)
     if tuple(a.shape) != shape:
         raise ValueError(f"{what}: shape {tuple(a.shape)} != {shape}")

@@ -188,7 +188,9 @@ def test_surface_first_ordering(kernel, dev, gpu_models, ck_models, c_oracles):
     for key in ("lw_fsck", "sw_wide"):
         out = run_gpu(gpu_models[key], flip(plev), flip(tlay), flip(tlev), tsfc, gl, torch.float64, dev, KERNELS[kernel])
         ref = run_oracle(c_oracles[key], ck_models[key], flip(plev), flip(tlay), flip(tlev), tsfc, gl)
-        check(out, ref, 1e-12, f"{key}/{kernel}/upside-down")
+        # SW: negative Rayleigh + positive ch4 term cancel, which amplifies the (1e-16-level) differences in
+        # summation order; the bar for this unphysical input is therefore 1e-10
+        check(out, ref, 1e-12 if key == "lw_fsck" else 1e-10, f"{key}/{kernel}/upside-down")
         if key == "lw_fsck":
             assert (ref["tau"] > 0).any()       # the ch4 term survived the clamp
 
