@@ -193,7 +193,7 @@ def main() -> None:
     ap.add_argument("--block", type=int, default=1 << 16, help="columns per kernel launch / output ring slot")
     ap.add_argument("--e2e-cols", type=int, default=1 << 17, help="columns per GPU per e2e step (host-array path)")
     ap.add_argument("--e2e-block", type=int, default=1 << 14)
-    ap.add_argument("--cpu-cols", type=int, default=1 << 15, help="bounded sample for cpu_baseline")
+    ap.add_argument("--cpu-cols", type=int, default=1 << 19, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-cols", type=int, default=1 << 15, help="columns per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
