@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -186,6 +187,9 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
         CUDA_TRY(cudaSetDevice(d.device));
         KernelArgs<Real> a{};
         a.ncol = ncol; a.nlay = nlay;
+#ifdef ECCKD_TUNE
+        a.dbg = getenv("ECCKD_DBG") ? atoi(getenv("ECCKD_DBG")) : 0;
+#endif
         a.plev = plev; a.tlay = tlay; a.tlev = tlev; a.tsfc = tsfc;
         a.out[0] = o0;
         if (sw) { a.out[1] = not_2str ? nullptr : o1; a.out[2] = not_2str ? nullptr : o2; a.out[3] = nullptr; a.out2d = not_2str ? nullptr : o2d; }
@@ -494,7 +498,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
                     for (int r = 0; r < t->nplanck; ++r)
                         for (int ln = 0; ln < kGP; ++ln)
                             if (grp * kGP + ln < ng)
-                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln] / (double)3.14159265359f;   // :288, folded into the table
+                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln];
             }
         }
         M->nslot_ = nslot; M->nv_lut_ = lut_gas >= 0 ? M->nv[lut_gas] : 0;

@@ -171,6 +171,10 @@ __device__ __forceinline__ double load_vmr(const GasRef &g, long long col, long 
 
 // streaming (evict-first) store: outputs are written once and never re-read here,
 // keep them from displacing the L2-resident tables
+#ifdef ECCKD_PLAIN_STORES
+template <typename Real> __device__ __forceinline__ void store_cs(Real *p, Real v) { *p = v; }
+#else
 template <typename Real> __device__ __forceinline__ void store_cs(Real *p, Real v) { __stcs(p, v); }
+#endif
 
 }  // namespace ecckd

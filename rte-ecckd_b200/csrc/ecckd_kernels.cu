@@ -221,6 +221,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Predicated global load that writes its destination register directly (tied operand): the refill of
+// the register cache stays branch-free and, more importantly, nothing has to wait for the data until
+// the value is really used one layer later (a compiler-generated load + MOV would stall on the MOV).
+__device__ __forceinline__ void ldg_if(double &dst, const double *p, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(dst) : "l"(p), "r"((int)pred));
+}
+__device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "+f"(dst) : "l"(p), "r"((int)pred));
+}
+
 // ============================================================================
 // walk_kernel: a three-role, warp-specialised pipeline inside one block
 //
@@ -259,6 +271,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     unsigned long long *bar_empty = bar_full + NBUF;
     unsigned long long *rec_full = bar_empty + NBUF;       // [2][TC]
     unsigned long long *rec_empty = rec_full + 2 * TC;     // [2][TC]
+    float *spl = reinterpret_cast<float *>(rec_empty + 2 * TC);   // LW: planck_function rows of this g-group, fp32 (exact)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
@@ -272,6 +285,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], NWW); }
         for (int q = 0; q < 2 * TC; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], 1); }
+    }
+    if (!SW) {   // Planck LUT of this g-group -> shared memory (29.6 KB for 231 rows): per-layer row reads become LDS
+        const float *src = m.wpl32 + (size_t)blockIdx.y * m.nplanck * kGP;
+        for (int q = threadIdx.x; q < m.nplanck * kGP; q += blockDim.x) spl[q] = src[q];
     }
     __syncthreads();
     const int nround = (nlay + 31) / 32;
@@ -292,7 +309,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             mbar_wait(&bar_full[b], u & 1);
             const Real *sb = stage + (size_t)b * TILE + c;
             const long long off0 = ((col0 + c) + (long long)ncol * lay0) * (long long)sizeof(Real) + plane * (g0 + gsub);
-            if (c_ok) {
+            if (c_ok && !(a.dbg & 1)) {
 #pragma unroll 2
                 for (int gi = 0; gi < 32 / GSTEP; ++gi) {
                     const int gg = gsub + gi * GSTEP;
@@ -332,7 +349,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             for (int cs = iw; cs < TC; cs += NI) {
                 const long long col = min(col0 + cs, (long long)ncol - 1);   // tail tiles recompute the last column; never stored
                 RecT rec;
-                if (j < nlay) {
+                if (j < nlay && !((a.dbg & 2) && r > 0)) {
                     const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
                     const double tl = (double)a.tlay[col + (long long)ncol * j];
                     const CellIndex ci = cell_index(m, pu, pl, tl);
@@ -377,16 +394,16 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         double a0, a1;
                         int itp = planck_index(m, tl, a0, a1);
                         rec.lay_off = (max(itp, 1) - 1) * kGP;
-                        rec.pa[0] = (Real)a0; rec.pa[1] = (Real)a1;
+                        rec.pa[0] = (Real)__ddiv_rn(a0, m.pi); rec.pa[1] = (Real)__ddiv_rn(a1, m.pi);
                         if (a.tlev) {
                             itp = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
                             rec.lev_off = (max(itp, 1) - 1) * kGP;
-                            rec.pa[2] = (Real)a0; rec.pa[3] = (Real)a1;
+                            rec.pa[2] = (Real)__ddiv_rn(a0, m.pi); rec.pa[3] = (Real)__ddiv_rn(a1, m.pi);
                         }
                     }
                 }
                 if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
-                if (j < nlay) recs[(rb * TC + cs) * 32 + lane] = rec;
+                if (j < nlay && !((a.dbg & 2) && r > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rec_full[rb * TC + cs]);
             }
@@ -401,7 +418,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const int ngroups = gridDim.y;
     const Real *wbil = TableOf<Real>::wbil(m) + (size_t)grp * m.nslot * kSlab + lane;
     const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
-    const Real *wpl = TableOf<Real>::wpl(m) + (size_t)grp * m.nplanck * kGP + lane;
+    const float *wpl = spl + lane;
     const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
 
     Real kb[NB][4];
@@ -414,25 +431,25 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     // (re)load the register cache for corner offsets (pkoff, hkoff); no-ops when unchanged
     auto refill = [&](int pkoff, int hkoff) {
-        if (pkoff != cur_pk) {
-            const bool shift = pkoff == cur_pk + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
+        if (a.dbg & 4) return;
+        const bool changed = pkoff != cur_pk;
+        const bool shift = pkoff == cur_pk + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
+        const bool full = changed && !shift;
 #pragma unroll
-            for (int s = 0; s < NB; ++s) {
-                if (s == 0 ? has_mix : s <= nvar) {
-                    const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + pkoff;
-                    if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
-                    else { kb[s][0] = k[kC00]; kb[s][2] = k[kC01]; }
-                    kb[s][1] = k[kC10]; kb[s][3] = k[kC11];
-                }
-            }
-            cur_pk = pkoff;
+        for (int s = 0; s < NB; ++s) {
+            const bool on = s == 0 ? has_mix : s <= nvar;
+            const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + pkoff;
+            if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
+            ldg_if(kb[s][0], k + kC00, full && on); ldg_if(kb[s][2], k + kC01, full && on);
+            ldg_if(kb[s][1], k + kC10, changed && on); ldg_if(kb[s][3], k + kC11, changed && on);
         }
-        if (has_lut && hkoff != cur_hk) {
-            const Real *k = wlut + hkoff;
-            kh[0] = k[kC00]; kh[1] = k[kC10]; kh[2] = k[kC01]; kh[3] = k[kC11];
-            kh[4] = k[kSlab + kC00]; kh[5] = k[kSlab + kC10]; kh[6] = k[kSlab + kC01]; kh[7] = k[kSlab + kC11];
-            cur_hk = hkoff;
-        }
+        cur_pk = pkoff;
+        const bool hchg = has_lut && hkoff != cur_hk;
+        const Real *k = wlut + hkoff;
+        ldg_if(kh[0], k + kC00, hchg); ldg_if(kh[1], k + kC10, hchg); ldg_if(kh[2], k + kC01, hchg); ldg_if(kh[3], k + kC11, hchg);
+        ldg_if(kh[4], k + kSlab + kC00, hchg); ldg_if(kh[5], k + kSlab + kC10, hchg);
+        ldg_if(kh[6], k + kSlab + kC01, hchg); ldg_if(kh[7], k + kSlab + kC11, hchg);
+        cur_hk = hkoff;
     };
 
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
@@ -440,8 +457,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     if (!SW && a.tlev) {
         double a0, a1;
         const int it = planck_index(m, (double)a.tlev[col], a0, a1);
-        const Real *p = wpl + (max(it, 1) - 1) * kGP;
-        lev_prev = (Real)a0 * p[0] + (Real)a1 * p[kGP];
+        const float *p = wpl + (max(it, 1) - 1) * kGP;
+        lev_prev = (Real)__ddiv_rn(a0, m.pi) * (Real)p[0] + (Real)__ddiv_rn(a1, m.pi) * (Real)p[kGP];
     }
 
     Real *st = stage + lane * TCP + warp;      // running staging pointer of this thread: + b*TILE + ls*ROWS
@@ -498,9 +515,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             } else {
                 Real p0, p1, p2, p3;
                 lds4<Real>(rp->pa, p0, p1, p2, p3);
-                const Real *pl = wpl + ix.z, *pv = wpl + ix.w;
-                const Real lay_src = p0 * pl[0] + p1 * pl[kGP];
-                const Real lev_next = p2 * pv[0] + p3 * pv[kGP];
+                const float *pl = wpl + ix.z, *pv = wpl + ix.w;
+                const Real lay_src = p0 * (Real)pl[0] + p1 * (Real)pl[kGP];
+                const Real lev_next = p2 * (Real)pv[0] + p3 * (Real)pv[kGP];
                 st[0] = tau;
                 st[1 * L * ROWS] = lay_src;
                 st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
@@ -527,8 +544,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         } else {
             double a0, a1;
             const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                            // :408-412
-            const Real *p = wpl + (max(it, 1) - 1) * kGP;
-            a.out2d[col + (long long)ncol * g] = (Real)a0 * p[0] + (Real)a1 * p[kGP];
+            const float *p = wpl + (max(it, 1) - 1) * kGP;
+            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * (Real)p[0] + (Real)__ddiv_rn(a1, m.pi) * (Real)p[kGP];
         }
     }
 }
@@ -570,7 +587,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
 {
     constexpr int NOUT = SW ? 2 : 4;
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * (TC + 1) +
-                        (2 * NBUF + 4 * TC) * sizeof(unsigned long long);
+                        (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float) * m.nplanck * kGP);
     auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -598,17 +615,17 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
 #ifdef ECCKD_TUNE
         static const int variant = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
         switch (variant) {   // NB, TC, L, NBUF, NI, NWW
-            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 3, 8, 2>(m, cg, a, mix, s);
-            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 2>(m, cg, a, mix, s);
-            case 3: return launch_walk_t<Real, SW, 2, 16, 2, 3, 2, 2>(m, cg, a, mix, s);
-            case 4: return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 2>(m, cg, a, mix, s);
-            case 5: return launch_walk_t<Real, SW, 2, 16, 2, 3, 4, 4>(m, cg, a, mix, s);
-            case 6: return launch_walk_t<Real, SW, 2, 8, 2, 3, 2, 1>(m, cg, a, mix, s);
-            case 7: return launch_walk_t<Real, SW, 2, 8, 2, 3, 4, 1>(m, cg, a, mix, s);
+            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 2, 8, 2>(m, cg, a, mix, s);
+            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 2, 2, 2>(m, cg, a, mix, s);
+            case 3: return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 2>(m, cg, a, mix, s);
+            case 4: return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 4>(m, cg, a, mix, s);
+            case 5: return launch_walk_t<Real, SW, 2, 16, 1, 3, 4, 2>(m, cg, a, mix, s);
             default: break;
         }
 #endif
-        return launch_walk_t<Real, SW, 2, 16, 2, 3, 4, 2>(m, cg, a, mix, s);
+        // LW keeps its Planck LUT in shared memory next to the records, so it has room for 2 staging tiles; SW for 4
+        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
+        else return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 4>(m, cg, a, mix, s);
     }
     return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1>(m, cg, a, mix, s);
 }

@@ -17,6 +17,7 @@ template <typename Real> struct KernelArgs {
     const Real *plev, *tlay, *tlev, *tsfc;
     Real *out[4];
     Real *out2d;
+    int dbg;   // experiment switches (ECCKD_DBG env, tuning builds only); 0 in production
 };
 
 // Bytes of stream-ordered scratch launch_walk needs for the per-call mixed table (0: none).
