@@ -22,6 +22,9 @@
 #include "ecckd_device.cuh"
 #include "ecckd_kernels.h"
 #include <cstdlib>
+#include <cstdint>
+#include <cuda.h>
+#include <cudaTypedefs.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace ecckd {
 
@@ -221,6 +224,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---- TMA (cp.async.bulk.tensor) store helpers ------------------------------------
+struct TmaMaps { alignas(64) CUtensorMap m[4]; };
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Predicated global load that writes its destination register directly (tied operand): the refill of
 // the register cache stays branch-free and, more importantly, nothing has to wait for the data until
 // the value is really used one layer later (a compiler-generated load + MOV would stall on the MOV).
@@ -253,21 +268,26 @@ __device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA>
 __global__ void __launch_bounds__((TC + NI + NWW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
-            const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab)
+            const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
 {
     constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled by the writers
-    constexpr int TCP = TC + 1;           // padded column stride: conflict-free transpose
+    // writer-warp path: padded column stride (conflict-free transpose both ways).
+    // TMA path: dense 128-byte rows [g][column] in the 128B-swizzle pattern the tensor map expects.
+    constexpr int TCP = TMA ? TC : TC + 1;
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
     constexpr int TILE = NOUT * L * ROWS; // one ring entry
     static_assert(TC % NI == 0, "every index warp serves TC/NI columns");
+    static_assert(!TMA || (L == 1 && NWW == 1 && sizeof(Real) * TC == 128), "TMA store path: one layer per tile, 128-byte rows, one store warp");
     using RecT = Rec<Real, NB>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // shared-memory carve-up (walk_smem_bytes() on the host mirrors it)
     RecT *recs = reinterpret_cast<RecT *>(smem_raw);                                  // [2][TC][32]
-    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * 2 * TC * 32);     // [NBUF][TILE]
-    unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(stage + (size_t)NBUF * TILE);
+    Real *stage = reinterpret_cast<Real *>(smem_raw + sizeof(RecT) * 2 * TC * 32);     // [NBUF][TILE]   (1024-byte aligned)
+    Real *zero_tile = stage + (size_t)NBUF * TILE;                                     // TMA && SW: source of the g = 0 plane
+    unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(zero_tile + ((TMA && SW) ? ROWS : 0));
     unsigned long long *bar_empty = bar_full + NBUF;
     unsigned long long *rec_full = bar_empty + NBUF;       // [2][TC]
     unsigned long long *rec_empty = rec_full + 2 * TC;     // [2][TC]
@@ -283,18 +303,43 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], NWW); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], TMA ? 1 : NWW); }
         for (int q = 0; q < 2 * TC; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], 1); }
     }
     if (!SW) {   // Planck LUT of this g-group -> shared memory (29.6 KB for 231 rows): per-layer row reads become LDS
         const float *src = m.wpl32 + (size_t)blockIdx.y * m.nplanck * kGP;
         for (int q = threadIdx.x; q < m.nplanck * kGP; q += blockDim.x) spl[q] = src[q];
     }
+    if (TMA && SW) {
+        for (int q = threadIdx.x; q < ROWS; q += blockDim.x) zero_tile[q] = 0;
+        fence_proxy_async_smem();
+    }
     __syncthreads();
     const int nround = (nlay + 31) / 32;
 
+    // =========================== TMA store warp ==================================
+    if (TMA && warp >= TC + NI) {
+        if (lane == 0) {
+            for (int n = 0; n < nlay; ++n) {            // one tile per layer
+                const int b = n % NBUF;
+                mbar_wait(&bar_full[b], (n / NBUF) & 1);
+                const Real *sb = stage + (size_t)b * TILE;
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o)
+                    if (a.out[o]) tma_store_3d(&maps.m[o], sb + o * ROWS, (int)col0, n, g0);
+                if (SW && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, (int)col0, n, g0);     // g = 0  :460
+                tma_commit();
+                if (n >= 1) { tma_wait_read<1>(); mbar_arrive(&bar_empty[(n - 1) % NBUF]); }   // previous tile has been read out
+            }
+            tma_wait_read<0>();
+            mbar_arrive(&bar_empty[(nlay - 1) % NBUF]);
+            tma_wait_all<0>();
+        }
+        return;
+    }
+
     // =========================== writer warps ====================================
-    if (warp >= TC + NI) {
+    if (!TMA && warp >= TC + NI) {
         constexpr int NWT = NWW * 32;                 // writer threads
         constexpr int GSTEP = NWT / TC;               // g-points covered per pass
         const int t = threadIdx.x - (TC + NI) * 32;
@@ -461,7 +506,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         lev_prev = (Real)__ddiv_rn(a0, m.pi) * (Real)p[0] + (Real)__ddiv_rn(a1, m.pi) * (Real)p[kGP];
     }
 
-    Real *st = stage + lane * TCP + warp;      // running staging pointer of this thread: + b*TILE + ls*ROWS
+    // running staging pointer of this thread: + b*TILE + ls*ROWS.  TMA: row = g-point (lane), 16-byte chunk
+    // XOR-swizzled with (row & 7) exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out
+    Real *st = TMA ? stage + lane * TC + ((((warp >> 1) ^ (lane & 7)) << 1) | (warp & 1)) : stage + lane * TCP + warp;
     int ls = 0, b = 0, fill = 0;               // layer inside the tile, ring slot, fills of slot 0 so far
     for (int r = 0; r < nround; ++r) {
         const int rb = r & 1;
@@ -526,6 +573,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             st += ROWS;
             if (++ls == L || (r == nround - 1 && l == len - 1)) {
+                if (TMA) fence_proxy_async_smem();     // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[b]);
                 st += TILE - ls * ROWS;
@@ -582,18 +630,54 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // ============================================================================
 // launchers
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW>
-static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s)
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    return fn;
+}
+
+// 3-D map of an (ncol, nlay, ngpt) fp64 output, box = 16 columns x 1 layer x 32 g-points, 128-byte swizzle
+static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay, int ngpt)
+{
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)ncol, (cuuint64_t)nlay, (cuuint64_t)ngpt};
+    const cuuint64_t gstr[2] = {(cuuint64_t)ncol * 8, (cuuint64_t)ncol * nlay * 8};
+    const cuuint32_t box[3] = {16, 1, 32}, estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false>
+static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
+                                 const TmaMaps *maps = nullptr)
 {
     constexpr int NOUT = SW ? 2 : 4;
-    const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * (TC + 1) +
+    constexpr int TCP = TMA ? TC : TC + 1;
+    const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
+                        ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
                         (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float) * m.nplanck * kGP);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW>;
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
-    kern<<<grid, (TC + NI + NWW) * 32, smem, s>>>(m, cg, a, mix);
+    static const TmaMaps no_maps{};
+    kern<<<grid, (TC + NI + NWW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
     return cudaGetLastError();
+}
+
+// The TMA store path needs fp64, 16-byte aligned outputs and a column pitch that is a multiple of 16 bytes.
+template <typename Real> static bool tma_eligible(const KernelArgs<Real> &a)
+{
+    if (sizeof(Real) != 8 || (a.ncol & 1)) return false;
+    for (int o = 0; o < 4; ++o) if (a.out[o] && (reinterpret_cast<uintptr_t>(a.out[o]) & 15)) return false;
+    return tensor_map_encoder() != nullptr;
 }
 
 size_t walk_scratch_bytes(const DevModel &m, const CallGases &, size_t real_size)
@@ -623,7 +707,21 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
             default: break;
         }
 #endif
-        // LW keeps its Planck LUT in shared memory next to the records, so it has room for 2 staging tiles; SW for 4
+        if constexpr (sizeof(Real) == 8) {
+            static const bool no_tma = getenv("ECCKD_NO_TMA") != nullptr;
+            if (!no_tma && tma_eligible(a)) {
+                // staging tiles leave the SM through cp.async.bulk.tensor: no writer warps, one tile per layer
+                TmaMaps maps{};
+                bool ok = true;
+                for (int o = 0; o < (SW ? 3 : 4); ++o)
+                    if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
+                if (ok) {
+                    if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true>(m, cg, a, mix, s, &maps);
+                }
+            }
+        }
+        // writer-warp path.  LW keeps its Planck LUT in shared memory next to the records: room for 2 staging tiles; SW for 4
         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
         else return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 4>(m, cg, a, mix, s);
     }
