@@ -518,6 +518,14 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         const int dev = devices ? devices[d] : d;
         if (dev < 0 || dev >= ndev_avail) { set_err(err, "ecckd_model_create: no such CUDA device"); return ECCKD_ERR_CUDA; }
         CUDA_TRY(cudaSetDevice(dev));
+        {   // per-call scratch comes from the stream-ordered pool: keep freed blocks cached instead of returning them to
+            // the driver at every synchronisation (the default release threshold is 0, which makes each call re-allocate)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
         std::unique_ptr<DevState> ds(new DevState);
         ds->device = dev;
         DevModel &dm = ds->dm;

@@ -329,10 +329,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     if (a.out[o]) tma_store_3d(&maps.m[o], sb + o * ROWS, (int)col0, n, g0);
                 if (SW && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, (int)col0, n, g0);     // g = 0  :460
                 tma_commit();
-                if (n >= 1) { tma_wait_read<1>(); mbar_arrive(&bar_empty[(n - 1) % NBUF]); }   // previous tile has been read out
+                tma_wait_read<0>();                     // the tile has been read out of shared memory: hand it back
+                mbar_arrive(&bar_empty[b]);
             }
-            tma_wait_read<0>();
-            mbar_arrive(&bar_empty[(nlay - 1) % NBUF]);
             tma_wait_all<0>();
         }
         return;
@@ -480,6 +479,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         const bool changed = pkoff != cur_pk;
         const bool shift = pkoff == cur_pk + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
         const bool full = changed && !shift;
+        if (changed) {
 #pragma unroll
         for (int s = 0; s < NB; ++s) {
             const bool on = s == 0 ? has_mix : s <= nvar;
@@ -488,12 +488,14 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             ldg_if(kb[s][0], k + kC00, full && on); ldg_if(kb[s][2], k + kC01, full && on);
             ldg_if(kb[s][1], k + kC10, changed && on); ldg_if(kb[s][3], k + kC11, changed && on);
         }
+        }
         cur_pk = pkoff;
-        const bool hchg = has_lut && hkoff != cur_hk;
-        const Real *k = wlut + hkoff;
-        ldg_if(kh[0], k + kC00, hchg); ldg_if(kh[1], k + kC10, hchg); ldg_if(kh[2], k + kC01, hchg); ldg_if(kh[3], k + kC11, hchg);
-        ldg_if(kh[4], k + kSlab + kC00, hchg); ldg_if(kh[5], k + kSlab + kC10, hchg);
-        ldg_if(kh[6], k + kSlab + kC01, hchg); ldg_if(kh[7], k + kSlab + kC11, hchg);
+        if (has_lut && hkoff != cur_hk) {
+            const Real *k = wlut + hkoff;
+            ldg_if(kh[0], k + kC00, true); ldg_if(kh[1], k + kC10, true); ldg_if(kh[2], k + kC01, true); ldg_if(kh[3], k + kC11, true);
+            ldg_if(kh[4], k + kSlab + kC00, true); ldg_if(kh[5], k + kSlab + kC10, true);
+            ldg_if(kh[6], k + kSlab + kC01, true); ldg_if(kh[7], k + kSlab + kC11, true);
+        }
         cur_hk = hkoff;
     };
 
@@ -548,12 +550,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 const Real *k = wmix + (size_t)ngroups * kSlab + (key & 0xffff);
                 tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
             }
-            // the cache is free now: start fetching the corners of the next layer so that
-            // their latency overlaps the Planck / staging work below
-            if (l + 1 < len) {
-                const int2 k1 = *reinterpret_cast<const int2 *>(&rp[1].key);
-                refill(k1.x & 0xffff, k1.y);
-            }
+            int2 k1 = make_int2(cur_pk, cur_hk);
+            if (l + 1 < len) k1 = *reinterpret_cast<const int2 *>(&rp[1].key);
+            constexpr bool early = !TMA || !SW;          // measured: LW prefers the early fetch, SW the late one
+            if (early) refill(k1.x & 0xffff, k1.y);     // cache is free: fetch the next layer's corners under the Planck / staging work
             if (SW) {
                 const Real ray = rp->pa[0] * sigma;             // :313-316
                 tau += ray;                                     // :456
@@ -576,6 +576,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (TMA) fence_proxy_async_smem();     // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[b]);
+                // TMA path: the proxy fence drains this thread's outstanding loads, so the next layer's corner
+                // fetch is issued after it (it then overlaps the next record read and Planck arithmetic)
+                if (!early) refill(k1.x & 0xffff, k1.y);
                 st += TILE - ls * ROWS;
                 ls = 0;
                 if (++b == NBUF) { b = 0; st -= NBUF * TILE; ++fill; }
@@ -717,7 +720,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
                     if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true>(m, cg, a, mix, s, &maps);
                 }
             }
         }

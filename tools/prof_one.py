@@ -20,9 +20,15 @@ lw = band == "lw"
 gases = ecckd_b200.PreparedGases(atm.gas_list(), ncol, 137, np.float64 if prec == "f64" else np.float32, dev)
 out = None
 k = {"walk": ecckd_b200.KERNEL_WALK, "generic": ecckd_b200.KERNEL_GENERIC}[kern]
+ts = []
 for r in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc if lw else None, gases, tlev=atm.tlev if lw else None, kernel=k, out=out)
     e1.record(); torch.cuda.synchronize()
-    print(f"{band} {prec} {kern} ncol={ncol}: {e0.elapsed_time(e1):.3f} ms")
+    ts.append(e0.elapsed_time(e1))
+ts = sorted(ts[1:]) if len(ts) > 1 else ts
+ng = go.get_ngpt(); w = 8 if prec == "f64" else 4
+byts = w * ncol * ((2 * 138 + 3 * 137 + 1) + (4 * 137 * ng + ng)) if lw else w * ncol * ((138 + 3 * 137) + (3 * 137 * ng + ng))
+med = ts[len(ts) // 2]
+print(f"{band} {prec} {kern} ncol={ncol}: min {ts[0]:.3f} ms  median {med:.3f} ms  ({byts / med / 1e6 / 6550.1 * 100:.1f}% of 6550 GB/s at median)")
