@@ -200,6 +200,36 @@ template <> __device__ __forceinline__ void lds2<float>(const float *p, float &a
     a = u.x; b = u.y;
 }
 
+// Explicit rounding / fusion: every instantiation of the walking kernel (TMA or writer-warp path, any tile
+// shape) must produce bit-identical values, so that column shards, host blocks and odd/even ncol agree bitwise.
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
+// a / b to within an ulp without the IEEE-division slow path: hardware reciprocal seed (20+ bits), two Newton steps,
+// one residual correction.  ssa = tau_rayleigh / tau only has to meet 1e-12, not correct rounding.
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = __fma_rn(r, __fma_rn(-b, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-b, r, 1.0), r);
+    const double q = __dmul_rn(a, r);
+    return __fma_rn(__fma_rn(-b, q, a), r, q);
+}
+__device__ __forceinline__ float div_fast(float a, float b) { return __fdiv_rn(a, b); }
+
+// c0*k0 + c1*k1 + c2*k2 + c3*k3 as one fused chain
+template <typename Real, typename K>
+__device__ __forceinline__ Real bil4(Real c0, Real c1, Real c2, Real c3, K k0, K k1, K k2, K k3)
+{
+    return fma_(c3, (Real)k3, fma_(c2, (Real)k2, fma_(c1, (Real)k1, mul_(c0, (Real)k0))));
+}
+
 // corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
 constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
 
@@ -268,8 +298,8 @@ __device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA>
-__global__ void __launch_bounds__((TC + NI + NWW) * 32, 1)
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW>
+__global__ void __launch_bounds__((TC / CPW + NI + NWW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
 {
@@ -279,7 +309,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     constexpr int TCP = TMA ? TC : TC + 1;
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
     constexpr int TILE = NOUT * L * ROWS; // one ring entry
+    constexpr int NCW = TC / CPW;          // compute warps
     static_assert(TC % NI == 0, "every index warp serves TC/NI columns");
+    static_assert(CPW == 1 || (CPW == 2 && TMA), "two columns per warp needs the 16-byte swizzled staging of the TMA path");
     static_assert(!TMA || (L == 1 && NWW == 1 && sizeof(Real) * TC == 128), "TMA store path: one layer per tile, 128-byte rows, one store warp");
     using RecT = Rec<Real, NB>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -303,7 +335,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], TC); mbar_init(&bar_empty[b], TMA ? 1 : NWW); }
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], NCW); mbar_init(&bar_empty[b], TMA ? 1 : NWW); }
         for (int q = 0; q < 2 * TC; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], 1); }
     }
     if (!SW) {   // Planck LUT of this g-group -> shared memory (29.6 KB for 231 rows): per-layer row reads become LDS
@@ -318,7 +350,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const int nround = (nlay + 31) / 32;
 
     // =========================== TMA store warp ==================================
-    if (TMA && warp >= TC + NI) {
+    if (TMA && warp >= NCW + NI) {
         if (lane == 0) {
             for (int n = 0; n < nlay; ++n) {            // one tile per layer
                 const int b = n % NBUF;
@@ -338,10 +370,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== writer warps ====================================
-    if (!TMA && warp >= TC + NI) {
+    if (!TMA && warp >= NCW + NI) {
         constexpr int NWT = NWW * 32;                 // writer threads
         constexpr int GSTEP = NWT / TC;               // g-points covered per pass
-        const int t = threadIdx.x - (TC + NI) * 32;
+        const int t = threadIdx.x - (NCW + NI) * 32;
         const int c = t % TC, gsub = t / TC;
         const bool c_ok = col0 + c < ncol;
         const long long plane = (long long)ncol * nlay * (long long)sizeof(Real);   // bytes between g-points
@@ -385,8 +417,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== index warps =====================================
-    if (warp >= TC) {
-        const int iw = warp - TC;
+    if (warp >= NCW) {
+        const int iw = warp - NCW;
         for (int r = 0; r < nround; ++r) {
             const int rb = r & 1, u = r >> 1;
             const int j = r * 32 + lane;
@@ -398,8 +430,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     const double tl = (double)a.tlay[col + (long long)ncol * j];
                     const CellIndex ci = cell_index(m, pu, pl, tl);
                     const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
-                    rec.c[0] = (Real)(tw0 * pw0); rec.c[1] = (Real)(tw0 * ci.pw1);
-                    rec.c[2] = (Real)(ci.tw1 * pw0); rec.c[3] = (Real)(ci.tw1 * ci.pw1);
+                    rec.c[0] = (Real)__dmul_rn(tw0, pw0); rec.c[1] = (Real)__dmul_rn(tw0, ci.pw1);
+                    rec.c[2] = (Real)__dmul_rn(ci.tw1, pw0); rec.c[3] = (Real)__dmul_rn(ci.tw1, ci.pw1);
                     const int ip = ci.ip0 - 1, it = ci.it0 - 1;
                     // Tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the per-g clamp
                     // (:233-238) becomes "skip the gas when its weight is negative"; NaN weights propagate.
@@ -456,120 +488,175 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== compute warps ===================================
-    const long long col = min(col0 + warp, (long long)ncol - 1);
-    const bool col_ok = col0 + warp < ncol;
+    // warp w owns columns CPW*w .. CPW*w + CPW-1 of the tile (CPW = 2: two independent dependency chains per
+    // lane, and the pair of values goes to the staging tile as one conflict-free 16-byte store)
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
     const int ngroups = gridDim.y;
-    const Real *wbil = TableOf<Real>::wbil(m) + (size_t)grp * m.nslot * kSlab + lane;
-    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
+    // The file tables are exact in fp32: the LUT gas and the varying gases are cached as fp32 rows (half the L1
+    // wavefronts of an fp64 row) and widened in the FMA chain (F2F has its own pipe); only the per-call mixed
+    // table, a sum of products, needs the full Real width.
+    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + lane;
+    const float *wlut = m.wlut32 + (size_t)grp * m.nv_lut * kSlab + lane;
     const float *wpl = spl + lane;
     const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
 
-    Real kb[NB][4];
-    Real kh[8];
+    Real km[CPW][4];                               // slot 0: mixed table
+    float kb[CPW][NB > 1 ? NB - 1 : 1][4];         // slots 1..NB-1: varying gases
+    float kh[CPW][8];
+    int cur_pk[CPW], cur_hk[CPW];
+    Real lev_prev[CPW];   // Planck source at the upper level of the current layer
+    long long col[CPW];
+    const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
 #pragma unroll
-    for (int s = 0; s < NB; ++s) kb[s][0] = kb[s][1] = kb[s][2] = kb[s][3] = 0;
+    for (int q = 0; q < CPW; ++q) {
+        km[q][0] = km[q][1] = km[q][2] = km[q][3] = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) kh[i] = 0;
-    int cur_pk = -0x10000, cur_hk = -0x10000;
+        for (int s = 0; s < NB - 1; ++s) kb[q][s][0] = kb[q][s][1] = kb[q][s][2] = kb[q][s][3] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) kh[q][i] = 0;
+        cur_pk[q] = cur_hk[q] = -0x10000;
+        col[q] = min(col0 + warp * CPW + q, (long long)ncol - 1);
+        lev_prev[q] = 0;
+        if (!SW && a.tlev) {
+            double a0, a1;
+            const int it = planck_index(m, (double)a.tlev[col[q]], a0, a1);
+            const float *p = wpl + (max(it, 1) - 1) * kGP;
+            lev_prev[q] = fma_((Real)__ddiv_rn(a1, m.pi), (Real)p[kGP], mul_((Real)__ddiv_rn(a0, m.pi), (Real)p[0]));
+        }
+    }
 
-    // (re)load the register cache for corner offsets (pkoff, hkoff); no-ops when unchanged
-    auto refill = [&](int pkoff, int hkoff) {
-        if (a.dbg & 4) return;
-        const bool changed = pkoff != cur_pk;
-        const bool shift = pkoff == cur_pk + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
+    // (re)load the register cache of column q for corner offsets (pkoff, hkoff); no-ops when unchanged
+    auto refill = [&](int q, int pkoff, int hkoff) {
+        const bool changed = pkoff != cur_pk[q];
+        const bool shift = pkoff == cur_pk[q] + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
         const bool full = changed && !shift;
         if (changed) {
+            {
+                const Real *k = wmix + pkoff;
+                if (shift) { km[q][0] = km[q][1]; km[q][2] = km[q][3]; }
+                ldg_if(km[q][0], k + kC00, full && has_mix); ldg_if(km[q][2], k + kC01, full && has_mix);
+                ldg_if(km[q][1], k + kC10, has_mix); ldg_if(km[q][3], k + kC11, has_mix);
+            }
 #pragma unroll
-        for (int s = 0; s < NB; ++s) {
-            const bool on = s == 0 ? has_mix : s <= nvar;
-            const Real *k = (s == 0 ? wmix : wbil + cg.var_off[s > 0 ? s - 1 : 0]) + pkoff;
-            if (shift) { kb[s][0] = kb[s][1]; kb[s][2] = kb[s][3]; }
-            ldg_if(kb[s][0], k + kC00, full && on); ldg_if(kb[s][2], k + kC01, full && on);
-            ldg_if(kb[s][1], k + kC10, changed && on); ldg_if(kb[s][3], k + kC11, changed && on);
+            for (int s = 0; s < NB - 1; ++s) {
+                const bool on = s < nvar;
+                const float *k = wbil + cg.var_off[s] + pkoff;
+                if (shift) { kb[q][s][0] = kb[q][s][1]; kb[q][s][2] = kb[q][s][3]; }
+                ldg_if(kb[q][s][0], k + kC00, full && on); ldg_if(kb[q][s][2], k + kC01, full && on);
+                ldg_if(kb[q][s][1], k + kC10, on); ldg_if(kb[q][s][3], k + kC11, on);
+            }
         }
+        cur_pk[q] = pkoff;
+        if (has_lut && hkoff != cur_hk[q]) {
+            const float *k = wlut + hkoff;
+            ldg_if(kh[q][0], k + kC00, true); ldg_if(kh[q][1], k + kC10, true); ldg_if(kh[q][2], k + kC01, true); ldg_if(kh[q][3], k + kC11, true);
+            ldg_if(kh[q][4], k + kSlab + kC00, true); ldg_if(kh[q][5], k + kSlab + kC10, true);
+            ldg_if(kh[q][6], k + kSlab + kC01, true); ldg_if(kh[q][7], k + kSlab + kC11, true);
         }
-        cur_pk = pkoff;
-        if (has_lut && hkoff != cur_hk) {
-            const Real *k = wlut + hkoff;
-            ldg_if(kh[0], k + kC00, true); ldg_if(kh[1], k + kC10, true); ldg_if(kh[2], k + kC01, true); ldg_if(kh[3], k + kC11, true);
-            ldg_if(kh[4], k + kSlab + kC00, true); ldg_if(kh[5], k + kSlab + kC10, true);
-            ldg_if(kh[6], k + kSlab + kC01, true); ldg_if(kh[7], k + kSlab + kC11, true);
-        }
-        cur_hk = hkoff;
+        cur_hk[q] = hkoff;
     };
-
-    const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
-    Real lev_prev = 0;   // Planck source at the upper level of the current layer
-    if (!SW && a.tlev) {
-        double a0, a1;
-        const int it = planck_index(m, (double)a.tlev[col], a0, a1);
-        const float *p = wpl + (max(it, 1) - 1) * kGP;
-        lev_prev = (Real)__ddiv_rn(a0, m.pi) * (Real)p[0] + (Real)__ddiv_rn(a1, m.pi) * (Real)p[kGP];
-    }
 
     // running staging pointer of this thread: + b*TILE + ls*ROWS.  TMA: row = g-point (lane), 16-byte chunk
     // XOR-swizzled with (row & 7) exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out
-    Real *st = TMA ? stage + lane * TC + ((((warp >> 1) ^ (lane & 7)) << 1) | (warp & 1)) : stage + lane * TCP + warp;
+    Real *st;
+    if (TMA) st = CPW == 2 ? stage + lane * TC + ((warp ^ (lane & 7)) << 1)
+                           : stage + lane * TC + ((((warp >> 1) ^ (lane & 7)) << 1) | (warp & 1));
+    else st = stage + lane * TCP + warp;
     int ls = 0, b = 0, fill = 0;               // layer inside the tile, ring slot, fills of slot 0 so far
     for (int r = 0; r < nround; ++r) {
         const int rb = r & 1;
         const int len = min(32, nlay - r * 32);
-        mbar_wait(&rec_full[rb * TC + warp], (r >> 1) & 1);
-        const RecT *rp = recs + (rb * TC + warp) * 32;
-        {
-            const int2 k0 = *reinterpret_cast<const int2 *>(&rp->key);
-            refill(k0.x & 0xffff, k0.y);
+        const RecT *rp[CPW];
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            mbar_wait(&rec_full[rb * TC + warp * CPW + q], (r >> 1) & 1);
+            rp[q] = recs + (rb * TC + warp * CPW + q) * 32;
+            const int2 k0 = *reinterpret_cast<const int2 *>(&rp[q]->key);
+            refill(q, k0.x & 0xffff, k0.y);
         }
-        for (int l = 0; l < len; ++l, ++rp) {
+        for (int l = 0; l < len; ++l) {
             if (ls == 0 && fill >= 1) mbar_wait(&bar_empty[b], (fill - 1) & 1);   // tile free again?
-            const int4 ix = *reinterpret_cast<const int4 *>(&rp->key);
-            Real c0, c1, c2, c3;
-            lds4<Real>(rp->c, c0, c1, c2, c3);
-            const int key = ix.x;
-            Real tau = 0;
-            if (key & kMaskLut) {
-                Real wl, v1;
-                lds2<Real>(&rp->wl, wl, v1);
-                const Real b0 = c0 * kh[0] + c1 * kh[1] + c2 * kh[2] + c3 * kh[3];
-                const Real b1 = c0 * kh[4] + c1 * kh[5] + c2 * kh[6] + c3 * kh[7];
-                tau = wl * (((Real)1 - v1) * b0 + v1 * b1);   // not b0 + v1*(b1-b0): that cancels when b1 << b0
+            Real val[NOUT][CPW];
+            int2 k1[CPW];
+            constexpr bool early = !TMA || !SW;          // measured: LW prefers the early fetch, SW the late one
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) {
+                const RecT *rq = rp[q];
+                const int4 ix = *reinterpret_cast<const int4 *>(&rq->key);
+                Real c0, c1, c2, c3;
+                lds4<Real>(rq->c, c0, c1, c2, c3);
+                const int key = ix.x;
+                Real tau = 0;
+                constexpr int kCommon = kMaskLut | (3 << kMaskShift);   // LUT gas + mixed table + one varying gas, all contributing
+                if (NB == 2 && (key & (kCommon | kMaskNeg)) == kCommon) {
+                    // the overwhelmingly common case as straight-line code: four independent bilinear chains
+                    Real wl, v1, w0, w1;
+                    lds2<Real>(&rq->wl, wl, v1);
+                    lds2<Real>(&rq->w[0], w0, w1);
+                    const Real b0 = bil4(c0, c1, c2, c3, kh[q][0], kh[q][1], kh[q][2], kh[q][3]);
+                    const Real b1 = bil4(c0, c1, c2, c3, kh[q][4], kh[q][5], kh[q][6], kh[q][7]);
+                    const Real bm = bil4(c0, c1, c2, c3, km[q][0], km[q][1], km[q][2], km[q][3]);
+                    const Real bv = bil4(c0, c1, c2, c3, kb[q][0][0], kb[q][0][1], kb[q][0][2], kb[q][0][3]);
+                    tau = mul_(wl, fma_(v1, b1, mul_(add_((Real)1, -v1), b0)));
+                    tau = fma_(w0, bm, tau);
+                    tau = fma_(w1, bv, tau);
+                } else {
+                    if (key & kMaskLut) {
+                        Real wl, v1;
+                        lds2<Real>(&rq->wl, wl, v1);
+                        const Real b0 = bil4(c0, c1, c2, c3, kh[q][0], kh[q][1], kh[q][2], kh[q][3]);
+                        const Real b1 = bil4(c0, c1, c2, c3, kh[q][4], kh[q][5], kh[q][6], kh[q][7]);
+                        // (1-v1)*b0 + v1*b1, not b0 + v1*(b1-b0): that cancels when b1 << b0
+                        tau = mul_(wl, fma_(v1, b1, mul_(add_((Real)1, -v1), b0)));
+                    }
+#pragma unroll
+                    for (int s = 0; s < NB; s += 2) {
+                        if (key & (3 << (s + kMaskShift))) {
+                            Real w0, w1;
+                            lds2<Real>(&rq->w[s], w0, w1);
+                            if (key & (1 << (s + kMaskShift))) {
+                                if (s == 0) tau = fma_(w0, bil4(c0, c1, c2, c3, km[q][0], km[q][1], km[q][2], km[q][3]), tau);
+                                else tau = fma_(w0, bil4(c0, c1, c2, c3, kb[q][s > 0 ? s - 1 : 0][0], kb[q][s > 0 ? s - 1 : 0][1],
+                                                         kb[q][s > 0 ? s - 1 : 0][2], kb[q][s > 0 ? s - 1 : 0][3]), tau);
+                            }
+                            if (key & (2 << (s + kMaskShift)))
+                                tau = fma_(w1, bil4(c0, c1, c2, c3, kb[q][s][0], kb[q][s][1], kb[q][s][2], kb[q][s][3]), tau);
+                        }
+                    }
+                    if (key & kMaskNeg) {   // upside-down layer: the negative-factor gases give positive optical depth
+                        const Real *k = wmix + (size_t)ngroups * kSlab + (key & 0xffff);
+                        tau = fma_(rq->w[0], bil4(c0, c1, c2, c3, k[kC00], k[kC10], k[kC01], k[kC11]), tau);
+                    }
+                }
+                k1[q] = make_int2(cur_pk[q], cur_hk[q]);
+                if (l + 1 < len) k1[q] = *reinterpret_cast<const int2 *>(&rq[1].key);
+                if (early) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
+                if (SW) {
+                    const Real ray = mul_(rq->pa[0], sigma);        // :313-316
+                    tau = add_(tau, ray);                           // :456
+                    val[0][q] = tau;
+                    val[1][q] = div_fast(ray, tau);                 // :459
+                } else {
+                    Real p0, p1, p2, p3;
+                    lds4<Real>(rq->pa, p0, p1, p2, p3);
+                    const float *pl = wpl + ix.z, *pv = wpl + ix.w;
+                    const Real lev_next = fma_(p3, (Real)pv[kGP], mul_(p2, (Real)pv[0]));
+                    val[0][q] = tau;
+                    val[1 % NOUT][q] = fma_(p1, (Real)pl[kGP], mul_(p0, (Real)pl[0]));
+                    val[2 % NOUT][q] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
+                    val[3 % NOUT][q] = lev_prev[q];     // lev_source_dec(:,j) = B(tlev(j))    :424
+                    lev_prev[q] = lev_next;
+                }
+                rp[q] = rq + 1;
             }
 #pragma unroll
-            for (int s = 0; s < NB; s += 2) {
-                if (key & (3 << (s + kMaskShift))) {
-                    Real w0, w1;
-                    lds2<Real>(&rp->w[s], w0, w1);
-                    if (key & (1 << (s + kMaskShift)))
-                        tau += w0 * (c0 * kb[s][0] + c1 * kb[s][1] + c2 * kb[s][2] + c3 * kb[s][3]);
-                    if (key & (2 << (s + kMaskShift)))
-                        tau += w1 * (c0 * kb[s + 1][0] + c1 * kb[s + 1][1] + c2 * kb[s + 1][2] + c3 * kb[s + 1][3]);
+            for (int o = 0; o < NOUT; ++o) {
+                if constexpr (CPW == 2) {
+                    if constexpr (sizeof(Real) == 8) *reinterpret_cast<double2 *>(st + o * L * ROWS) = make_double2((double)val[o][0], (double)val[o][1]);
+                    else *reinterpret_cast<float2 *>(st + o * L * ROWS) = make_float2((float)val[o][0], (float)val[o][1]);
+                } else {
+                    st[o * L * ROWS] = val[o][0];
                 }
-            }
-            if (key & kMaskNeg) {   // upside-down layer: the negative-factor gases give positive optical depth
-                const Real *k = wmix + (size_t)ngroups * kSlab + (key & 0xffff);
-                tau += rp->w[0] * (c0 * k[kC00] + c1 * k[kC10] + c2 * k[kC01] + c3 * k[kC11]);
-            }
-            int2 k1 = make_int2(cur_pk, cur_hk);
-            if (l + 1 < len) k1 = *reinterpret_cast<const int2 *>(&rp[1].key);
-            constexpr bool early = !TMA || !SW;          // measured: LW prefers the early fetch, SW the late one
-            if (early) refill(k1.x & 0xffff, k1.y);     // cache is free: fetch the next layer's corners under the Planck / staging work
-            if (SW) {
-                const Real ray = rp->pa[0] * sigma;             // :313-316
-                tau += ray;                                     // :456
-                st[0] = tau;
-                st[L * ROWS] = ray / tau;                       // :459
-            } else {
-                Real p0, p1, p2, p3;
-                lds4<Real>(rp->pa, p0, p1, p2, p3);
-                const float *pl = wpl + ix.z, *pv = wpl + ix.w;
-                const Real lay_src = p0 * (Real)pl[0] + p1 * (Real)pl[kGP];
-                const Real lev_next = p2 * (Real)pv[0] + p3 * (Real)pv[kGP];
-                st[0] = tau;
-                st[1 * L * ROWS] = lay_src;
-                st[2 * L * ROWS] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
-                st[3 * L * ROWS] = lev_prev;        // lev_source_dec(:,j) = B(tlev(j))    :424
-                lev_prev = lev_next;
             }
             st += ROWS;
             if (++ls == L || (r == nround - 1 && l == len - 1)) {
@@ -578,25 +665,34 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (lane == 0) mbar_arrive(&bar_full[b]);
                 // TMA path: the proxy fence drains this thread's outstanding loads, so the next layer's corner
                 // fetch is issued after it (it then overlaps the next record read and Planck arithmetic)
-                if (!early) refill(k1.x & 0xffff, k1.y);
+                if (!early) {
+#pragma unroll
+                    for (int q = 0; q < CPW; ++q) refill(q, k1[q].x & 0xffff, k1[q].y);
+                }
                 st += TILE - ls * ROWS;
                 ls = 0;
                 if (++b == NBUF) { b = 0; st -= NBUF * TILE; ++fill; }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rec_empty[rb * TC + warp]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) mbar_arrive(&rec_empty[rb * TC + warp * CPW + q]);
+        }
     }
 
     // ---- per-column 2-D outputs -------------------------------------------------
-    if (col_ok && g0 + lane < ngpt && a.out2d) {
-        if (SW) {
-            a.out2d[col + (long long)ncol * g] = (Real)m.solar[g];                                  // :468-472
-        } else {
-            double a0, a1;
-            const int it = planck_index(m, (double)a.tsfc[col], a0, a1);                            // :408-412
-            const float *p = wpl + (max(it, 1) - 1) * kGP;
-            a.out2d[col + (long long)ncol * g] = (Real)__ddiv_rn(a0, m.pi) * (Real)p[0] + (Real)__ddiv_rn(a1, m.pi) * (Real)p[kGP];
+#pragma unroll
+    for (int q = 0; q < CPW; ++q) {
+        if (col0 + warp * CPW + q < ncol && g0 + lane < ngpt && a.out2d) {
+            if (SW) {
+                a.out2d[col[q] + (long long)ncol * g] = (Real)m.solar[g];                                  // :468-472
+            } else {
+                double a0, a1;
+                const int it = planck_index(m, (double)a.tsfc[col[q]], a0, a1);                            // :408-412
+                const float *p = wpl + (max(it, 1) - 1) * kGP;
+                a.out2d[col[q] + (long long)ncol * g] = fma_((Real)__ddiv_rn(a1, m.pi), (Real)p[kGP], mul_((Real)__ddiv_rn(a0, m.pi), (Real)p[0]));
+            }
         }
     }
 }
@@ -657,7 +753,7 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
                                  const TmaMaps *maps = nullptr)
 {
@@ -666,12 +762,12 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
                         ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
                         (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float) * m.nplanck * kGP);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA>;
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
     static const TmaMaps no_maps{};
-    kern<<<grid, (TC + NI + NWW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
+    kern<<<grid, (TC / CPW + NI + NWW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
     return cudaGetLastError();
 }
 
@@ -719,8 +815,15 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                 for (int o = 0; o < (SW ? 3 : 4); ++o)
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
-                    if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true>(m, cg, a, mix, s, &maps);
+#ifdef ECCKD_TUNE
+                    static const int cpw = getenv("ECCKD_CPW") ? atoi(getenv("ECCKD_CPW")) : 2;
+                    if (cpw == 1) {
+                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
+                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    }
+#endif
+                    if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 2>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true, 2>(m, cg, a, mix, s, &maps);
                 }
             }
         }
