@@ -816,6 +816,15 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
 #ifdef ECCKD_TUNE
+                    static const int ni = getenv("ECCKD_NI") ? atoi(getenv("ECCKD_NI")) : 4;
+                    if (ni == 2) {
+                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 2, 1, true, 1>(m, cg, a, mix, s, &maps);
+                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 2, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    }
+                    if (ni == 8) {
+                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
+                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    }
                     static const int cpw = getenv("ECCKD_CPW") ? atoi(getenv("ECCKD_CPW")) : 1;
                     if (cpw == 2) {
                         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 2>(m, cg, a, mix, s, &maps);
@@ -823,8 +832,9 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     }
 #endif
                     // one column per compute warp (16 warps): measured faster than two columns x 8 warps (ECCKD_CPW=2 in tuning builds)
+                    // LW records carry the Planck indices too (two more IEEE divisions per level): 8 index warps keep ahead
                     if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
                 }
             }
         }

@@ -337,3 +337,25 @@ def test_linearity_in_a_linear_gas(dev, gpu_models):
     t0, t1, t2 = tau(0.0), tau(1.0), tau(2.0)
     d1, d2 = t1 - t0, t2 - t1
     assert np.max(np.abs(d2 - d1) / np.maximum(t2, 1e-300)) <= 1e-13
+
+
+# ---- downstream fluxes (north_star: within 0.01 W m-2) ------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_downstream_fluxes_within_0p01_wm2(dtype, dev, gpu_models, ck_models, c_oracles):
+    """The same flux solver (tests/rte_solvers.py: the rte-rrtmgp formulation, which is not available offline) applied
+    to the oracle's and to the GPU's optical properties and sources: broadband fluxes agree to < 0.01 W m-2,
+    for the fp64 path and for the fp32 variant."""
+    import rte_solvers
+    inp = atm_numpy(synthetic.make_atmosphere(64, 137, col0=4242))
+    out = run_gpu(gpu_models["lw_fsck"], *inp, dtype, dev)
+    ref = run_oracle(c_oracles["lw_fsck"], ck_models["lw_fsck"], *inp)     # fp64 oracle on the fp64 inputs
+    f = lambda d: rte_solvers.lw_fluxes(*(np.asarray(d[k], dtype=np.float64) for k in ("tau", "lay_source", "lev_source_inc", "lev_source_dec", "sfc_source")))
+    (up_g, dn_g), (up_r, dn_r) = f(out), f(ref)
+    assert 150 < up_r[:, 0].mean() < 400 and 150 < dn_r[:, -1].mean() < 500        # sane OLR / surface downwelling
+    assert max(np.abs(up_g - up_r).max(), np.abs(dn_g - dn_r).max()) < 0.01
+    out = run_gpu(gpu_models["sw_wide"], *inp, dtype, dev)
+    ref = run_oracle(c_oracles["sw_wide"], ck_models["sw_wide"], *inp)
+    f = lambda d: rte_solvers.sw_fluxes(*(np.asarray(d[k], dtype=np.float64) for k in ("tau", "ssa", "g", "toa_src")))
+    sg, sr = f(out), f(ref)
+    assert 500 < sr[1][:, -1].mean() < 820                                           # surface insolation at mu0 = 0.6
+    assert max(np.abs(a - b).max() for a, b in zip(sg, sr)) < 0.01
