@@ -194,6 +194,8 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
         a.out[0] = o0;
         if (sw) { a.out[1] = not_2str ? nullptr : o1; a.out[2] = not_2str ? nullptr : o2; a.out[3] = nullptr; a.out2d = not_2str ? nullptr : o2d; }
         else { a.out[1] = o1; a.out[2] = lev_missing ? nullptr : o2; a.out[3] = lev_missing ? nullptr : o3; a.out2d = o2d; }
+        // the walking kernel indexes outputs with 32-bit element offsets
+        if ((long long)ncol * nlay * M->ngpt >= (1ll << 31)) walk_ok = false;
         bool use_walk;
         if (kernel == ECCKD_KERNEL_AUTO) use_walk = walk_ok;
         else if (kernel == ECCKD_KERNEL_WALK) {
@@ -459,7 +461,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
     // Qualifies when extents fit the padding, at most one look-up-table gas, at most
     // kMaxBil distinct bilinear tables, and no negative coefficient (so that the
     // per-g clamp :233-238 reduces to a per-gas sign test of the weight).
-    std::vector<double> wbil64, wlut64, wpl64;
+    std::vector<double> wbil64, wlut64;
     {
         int nlut = 0, lut_gas = -1, nslot = 0;
         std::vector<long long> slot_off;
@@ -492,19 +494,11 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
                                     k64[M->table_off[lut_gas] + src + (size_t)ng * np * nt * iv];
                         }
                 }
-            if (!t->shortwave) {
-                wpl64.assign((size_t)ngroups * t->nplanck * kGP, 0.0);
-                for (int grp = 0; grp < ngroups; ++grp)
-                    for (int r = 0; r < t->nplanck; ++r)
-                        for (int ln = 0; ln < kGP; ++ln)
-                            if (grp * kGP + ln < ng)
-                                wpl64[((size_t)grp * t->nplanck + r) * kGP + ln] = t->planck_function[(size_t)ng * r + grp * kGP + ln];
-            }
         }
         M->nslot_ = nslot; M->nv_lut_ = lut_gas >= 0 ? M->nv[lut_gas] : 0;
     }
     auto narrow = [](const std::vector<double> &v) { std::vector<float> f(v.size()); for (size_t q = 0; q < v.size(); ++q) f[q] = (float)v[q]; return f; };
-    const std::vector<float> wbil32 = narrow(wbil64), wlut32 = narrow(wlut64), wpl32 = narrow(wpl64);
+    const std::vector<float> wbil32 = narrow(wbil64), wlut32 = narrow(wlut64);
     std::vector<double> tbase(t->temperature, t->temperature + t->npress);               // temperature(:,1)
     std::vector<double> ray, sol;
     if (t->shortwave) {
@@ -551,11 +545,9 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         d2.dm.nslot = M->nslot_; d2.dm.nv_lut = M->nv_lut_;
         if ((rc = upload(d2, wbil64, &d2.dm.wbil64, err))) return rc;
         if ((rc = upload(d2, wlut64, &d2.dm.wlut64, err))) return rc;
-        if ((rc = upload(d2, wpl64, &d2.dm.wpl64, err))) return rc;
         if (M->fp32_exact) {
             if ((rc = upload(d2, wbil32, &d2.dm.wbil32, err))) return rc;
             if ((rc = upload(d2, wlut32, &d2.dm.wlut32, err))) return rc;
-            if ((rc = upload(d2, wpl32, &d2.dm.wpl32, err))) return rc;
         }
     }
     *out = M.release();

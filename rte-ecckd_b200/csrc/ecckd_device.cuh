@@ -46,10 +46,9 @@ struct DevModel {
     // walk tables (NULL when the model does not qualify): per g-group of 32,
     //   wbil [group][slot][ip][it][lane]   slot = distinct bilinear table, model order, composite once
     //   wlut [group][iv][ip][it][lane]     the single look-up-table gas
-    //   wpl  [group][itp][lane]            planck_function
     int nslot, nv_lut;
-    const double *wbil64, *wlut64, *wpl64;
-    const float *wbil32, *wlut32, *wpl32;
+    const double *wbil64, *wlut64;
+    const float *wbil32, *wlut32;
 };
 
 // One active gas of this call, already resolved against the model on the host
@@ -90,14 +89,12 @@ template <> struct TableOf<double> {
     __device__ static const double *planck(const DevModel &m) { return m.planck64; }
     __device__ static const double *wbil(const DevModel &m) { return m.wbil64; }
     __device__ static const double *wlut(const DevModel &m) { return m.wlut64; }
-    __device__ static const double *wpl(const DevModel &m) { return m.wpl64; }
 };
 template <> struct TableOf<float> {
     __device__ static const float *k(const DevModel &m) { return m.k32; }
     __device__ static const float *planck(const DevModel &m) { return m.planck32; }
     __device__ static const float *wbil(const DevModel &m) { return m.wbil32; }
     __device__ static const float *wlut(const DevModel &m) { return m.wlut32; }
-    __device__ static const float *wpl(const DevModel &m) { return m.wpl32; }
 };
 
 // ---- per-cell interpolation state (pressure, temperature) -------------------

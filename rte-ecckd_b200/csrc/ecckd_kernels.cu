@@ -166,14 +166,12 @@ mix_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases
 // address: one wavefront per 16-byte vector load).
 template <typename Real, int NB> struct alignas(16) Rec {
     Real c[4];          // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
-    Real pa[4];         // LW: lay (a0,a1), lower level (a0,a1) [table is pre-divided by pi].  SW: pa[0] = moles_per_layer
-    Real w[NB];         // w[0] = simple_weight (mixed table); w[s] = weight of varying gas s-1
+    Real w[NB];         // w[0] = simple_weight (mixed table; also SW's moles_per_layer); w[s] = weight of varying gas s-1
     Real wl, vw1;       // LUT gas: weight, vmr_weight1
     alignas(16) int key;// bilinear corner offset (ip*kNTP + it)*kGP  |  mask << 16
                         //   mask bit s: slot s contributes; bit 8: LUT gas; bit 9: negative-weight mix (slow path)
     int hkoff;          // LUT corner offset ((iv*kNPP + ip)*kNTP + it)*kGP
-    int lay_off;        // Planck row offset of the layer temperature      (row*kGP)
-    int lev_off;        // Planck row offset of the lower-level temperature
+    int pad0, pad1;
 };
 constexpr int kMaskShift = 16, kMaskLut = 0x100 << kMaskShift, kMaskNeg = 0x200 << kMaskShift;
 
@@ -298,19 +296,21 @@ __device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW>
-__global__ void __launch_bounds__((TC / CPW + NI + NWW) * 32, 1)
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW>
+__global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
 {
-    constexpr int NOUT = SW ? 2 : 4;      // staged outputs; SW's g plane is zero-filled by the writers
+    constexpr int NOUT = SW ? 2 : 1;      // staged outputs: tau (+ ssa).  SW's g plane is zero-filled by the store warp;
+                                          // LW's three Planck sources are written by the Planck warps, straight to global memory
+    static_assert(SW ? NPW == 0 : NPW >= 1, "longwave needs Planck warps, shortwave has none");
     // writer-warp path: padded column stride (conflict-free transpose both ways).
     // TMA path: dense 128-byte rows [g][column] in the 128B-swizzle pattern the tensor map expects.
     constexpr int TCP = TMA ? TC : TC + 1;
     constexpr int ROWS = 32 * TCP;        // one (output, layer) tile: 32 g-points x TC columns
     constexpr int TILE = NOUT * L * ROWS; // one ring entry
     constexpr int NCW = TC / CPW;          // compute warps
-    static_assert(TC % NI == 0, "every index warp serves TC/NI columns");
+    
     static_assert(CPW == 1 || (CPW == 2 && TMA), "two columns per warp needs the 16-byte swizzled staging of the TMA path");
     static_assert(!TMA || (L == 1 && NWW == 1 && sizeof(Real) * TC == 128), "TMA store path: one layer per tile, 128-byte rows, one store warp");
     using RecT = Rec<Real, NB>;
@@ -323,9 +323,13 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     unsigned long long *bar_empty = bar_full + NBUF;
     unsigned long long *rec_full = bar_empty + NBUF;       // [2][TC]
     unsigned long long *rec_empty = rec_full + 2 * TC;     // [2][TC]
-    float *spl = reinterpret_cast<float *>(rec_empty + 2 * TC);   // LW: planck_function rows of this g-group, fp32 (exact)
+    float *spl = reinterpret_cast<float *>(rec_empty + 2 * TC);   // LW: planck_function of this g-group, fp32 (exact), [g][row]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Roles are laid out in LOGICAL warp order [compute | index | store | Planck]; hardware warp ids run the other way
+    // round because the SM's issue arbiter prefers the highest warp id: the latency-bound compute warps get priority
+    // over the throughput-oriented Planck warps.
+    constexpr int NWARPS = TC / CPW + NI + NWW + NPW;
+    const int warp = NWARPS - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
     const long long col0 = (long long)blockIdx.x * TC;
     const int ngpt = m.ngpt;
@@ -338,9 +342,18 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         for (int b = 0; b < NBUF; ++b) { mbar_init(&bar_full[b], NCW); mbar_init(&bar_empty[b], TMA ? 1 : NWW); }
         for (int q = 0; q < 2 * TC; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], 1); }
     }
-    if (!SW) {   // Planck LUT of this g-group -> shared memory (29.6 KB for 231 rows): per-layer row reads become LDS
-        const float *src = m.wpl32 + (size_t)blockIdx.y * m.nplanck * kGP;
-        for (int q = threadIdx.x; q < m.nplanck * kGP; q += blockDim.x) spl[q] = src[q];
+    if (!SW) {   // Planck LUT of this g-group -> shared memory, transposed to [g][row] (29.6 KB for 231 rows): the Planck
+                 // warps (lanes = columns) gather rows that differ per lane, which then fall into different banks
+        // each entry holds the row AND its upper neighbour, so one 8-byte LDS fetches both interpolation operands
+        const int np_ = m.nplanck;
+        float2 *spl2 = reinterpret_cast<float2 *>(spl);
+        for (int q = threadIdx.x; q < np_ * kGP; q += blockDim.x) {
+            const int row = q / kGP, gl = q % kGP;
+            const bool gok = g0 + gl < ngpt;
+            const float p0 = gok ? m.planck32[(size_t)row * ngpt + g0 + gl] : 0.0f;
+            const float p1 = (gok && row + 1 < np_) ? m.planck32[(size_t)(row + 1) * ngpt + g0 + gl] : 0.0f;
+            spl2[gl * np_ + row] = make_float2(p0, p1);
+        }
     }
     if (TMA && SW) {
         for (int q = threadIdx.x; q < ROWS; q += blockDim.x) zero_tile[q] = 0;
@@ -349,8 +362,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     __syncthreads();
     const int nround = (nlay + 31) / 32;
 
+    if ((a.dbg & 128) && warp < NCW + NI + NWW) return;   // experiment: Planck warps only
     // =========================== TMA store warp ==================================
-    if (TMA && warp >= NCW + NI) {
+    if (TMA && warp >= NCW + NI && warp < NCW + NI + NWW) {
         if (lane == 0) {
             for (int n = 0; n < nlay; ++n) {            // one tile per layer
                 const int b = n % NBUF;
@@ -370,10 +384,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== writer warps ====================================
-    if (!TMA && warp >= NCW + NI) {
+    if (!TMA && warp >= NCW + NI && warp < NCW + NI + NWW) {
         constexpr int NWT = NWW * 32;                 // writer threads
         constexpr int GSTEP = NWT / TC;               // g-points covered per pass
-        const int t = threadIdx.x - (NCW + NI) * 32;
+        const int t = (warp - (NCW + NI)) * 32 + lane;
         const int c = t % TC, gsub = t / TC;
         const bool c_ok = col0 + c < ncol;
         const long long plane = (long long)ncol * nlay * (long long)sizeof(Real);   // bytes between g-points
@@ -416,8 +430,88 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         return;
     }
 
+    // =========================== Planck warps (LW) ===============================
+    // lanes = (column, layer): a unit is TC columns x 32/TC layers.  Per g-point every lane interpolates its own
+    // rows of the shared-memory LUT and the warp stores full 128-byte column runs of lay_source,
+    // lev_source_inc and lev_source_dec directly -- these three outputs (75 % of the longwave bytes) never
+    // touch the staging tiles.  inc(:,j) and dec(:,j+1) are the same expression of the same level
+    // temperature, hence bitwise equal, as when the reference copies one buffer twice (:423-424).
+    if (!SW && warp >= NCW + NI + NWW) {
+        if (a.dbg & 64) return;
+        constexpr int LPU = 32 / TC;                  // layers per unit
+        const int pw = warp - (NCW + NI + NWW);
+        const int c = lane % TC, lsel = lane / TC;
+        const bool c_ok = col0 + c < ncol;
+        const long long colp = min(col0 + c, (long long)ncol - 1);
+        const int ng = min(kGP, ngpt - g0);
+        const int S = m.nplanck;
+        const long long plane = (long long)ncol * nlay;          // elements between g-points
+        const bool has_lev = a.tlev != nullptr;
+        // software pipeline: the temperatures of the next unit are fetched before the g-loop of the current one
+        auto fetch = [&](int u, double &tl, double &tu, double &td) {
+            const int jj = min(u * LPU + lsel, nlay - 1);
+            tl = (double)a.tlay[colp + (long long)ncol * jj];
+            tu = td = 0.0;
+            if (has_lev) { tu = (double)a.tlev[colp + (long long)ncol * jj]; td = (double)a.tlev[colp + (long long)ncol * (jj + 1)]; }
+        };
+        double tl_n, tu_n, td_n;
+        if (pw * LPU < nlay) fetch(pw, tl_n, tu_n, td_n);
+        const unsigned plane32 = (unsigned)plane;            // elements between g-points (the walking kernel needs ncol*nlay*ngpt < 2^31)
+        for (int u = pw; u * LPU < nlay; u += NPW) {
+            const int j = u * LPU + lsel;
+            const bool ok = c_ok && j < nlay;
+            const int jj = min(j, nlay - 1);
+            const double tl = tl_n, tu = tu_n, td = td_n;
+            if ((u + NPW) * LPU < nlay) fetch(u + NPW, tl_n, tu_n, td_n);
+            double a0, a1;
+            int it = planck_index(m, tl, a0, a1);
+            const float2 *tl_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
+            const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
+            const unsigned o = (unsigned)(colp + (long long)ncol * jj) + plane32 * (unsigned)g0;
+            if (has_lev) {
+                it = planck_index(m, tu, a0, a1);
+                const float2 *tu_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
+                const Real u0 = (Real)__ddiv_rn(a0, m.pi), u1 = (Real)__ddiv_rn(a1, m.pi);
+                it = planck_index(m, td, a0, a1);
+                const float2 *td_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
+                const Real d0 = (Real)__ddiv_rn(a0, m.pi), d1 = (Real)__ddiv_rn(a1, m.pi);
+                unsigned off = o;
+                int so = 0;
+#pragma unroll 4
+                for (int gq = 0; gq < ng; ++gq, off += plane32, so += S) {
+                    const float2 pl = tl_p[so], pd = td_p[so], pu = tu_p[so];
+                    const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
+                    const Real vi = fma_(d1, (Real)pd.y, mul_(d0, (Real)pd.x));      // lev_source_inc(:,j) = B(tlev(j+1))  :423
+                    const Real vd = fma_(u1, (Real)pu.y, mul_(u0, (Real)pu.x));      // lev_source_dec(:,j) = B(tlev(j))    :424
+                    if (ok) { store_cs(a.out[1] + off, vl); store_cs(a.out[2] + off, vi); store_cs(a.out[3] + off, vd); }
+                }
+            } else {
+                unsigned off = o;
+                int so = 0;
+#pragma unroll 4
+                for (int gq = 0; gq < ng; ++gq, off += plane32, so += S) {
+                    const float2 pl = tl_p[so];
+                    const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
+                    if (ok) store_cs(a.out[1] + off, vl);
+                }
+            }
+        }
+        if (pw == 0 && a.out2d) {                      // sfc_source(:, g) = B(tsfc)   :408-412
+            double a0, a1;
+            const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
+            const int r = max(it, 1) - 1;
+            const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
+            for (int gq = lsel; gq < ng; gq += LPU)
+                if (c_ok) {
+                    const float2 ps = reinterpret_cast<const float2 *>(spl)[gq * S + r];
+                    a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, (Real)ps.y, mul_(s0, (Real)ps.x));
+                }
+        }
+        return;
+    }
+
     // =========================== index warps =====================================
-    if (warp >= NCW) {
+    if (warp >= NCW && warp < NCW + NI) {
         const int iw = warp - NCW;
         for (int r = 0; r < nround; ++r) {
             const int rb = r & 1, u = r >> 1;
@@ -462,21 +556,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         if (!(wd < 0.0)) mask |= 0x100;
                     }
                     rec.key = (ip * kNTP + it) * kGP | mask << kMaskShift;
-                    rec.pa[0] = rec.pa[1] = rec.pa[2] = rec.pa[3] = 0;
-                    rec.lay_off = rec.lev_off = 0;
-                    if (SW) {
-                        rec.pa[0] = (Real)ci.sw;   // moles_per_layer == simple_weight (:143 vs :313-314, same product)
-                    } else {
-                        double a0, a1;
-                        int itp = planck_index(m, tl, a0, a1);
-                        rec.lay_off = (max(itp, 1) - 1) * kGP;
-                        rec.pa[0] = (Real)__ddiv_rn(a0, m.pi); rec.pa[1] = (Real)__ddiv_rn(a1, m.pi);
-                        if (a.tlev) {
-                            itp = planck_index(m, (double)a.tlev[col + (long long)ncol * (j + 1)], a0, a1);
-                            rec.lev_off = (max(itp, 1) - 1) * kGP;
-                            rec.pa[2] = (Real)__ddiv_rn(a0, m.pi); rec.pa[3] = (Real)__ddiv_rn(a1, m.pi);
-                        }
-                    }
+                    rec.pad0 = rec.pad1 = 0;
                 }
                 if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
                 if (j < nlay && !((a.dbg & 2) && r > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
@@ -497,14 +577,12 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // table, a sum of products, needs the full Real width.
     const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + lane;
     const float *wlut = m.wlut32 + (size_t)grp * m.nv_lut * kSlab + lane;
-    const float *wpl = spl + lane;
     const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
 
     Real km[CPW][4];                               // slot 0: mixed table
     float kb[CPW][NB > 1 ? NB - 1 : 1][4];         // slots 1..NB-1: varying gases
     float kh[CPW][8];
     int cur_pk[CPW], cur_hk[CPW];
-    Real lev_prev[CPW];   // Planck source at the upper level of the current layer
     long long col[CPW];
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
 #pragma unroll
@@ -516,13 +594,6 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         for (int i = 0; i < 8; ++i) kh[q][i] = 0;
         cur_pk[q] = cur_hk[q] = -0x10000;
         col[q] = min(col0 + warp * CPW + q, (long long)ncol - 1);
-        lev_prev[q] = 0;
-        if (!SW && a.tlev) {
-            double a0, a1;
-            const int it = planck_index(m, (double)a.tlev[col[q]], a0, a1);
-            const float *p = wpl + (max(it, 1) - 1) * kGP;
-            lev_prev[q] = fma_((Real)__ddiv_rn(a1, m.pi), (Real)p[kGP], mul_((Real)__ddiv_rn(a0, m.pi), (Real)p[0]));
-        }
     }
 
     // (re)load the register cache of column q for corner offsets (pkoff, hkoff); no-ops when unchanged
@@ -632,20 +703,12 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (l + 1 < len) k1[q] = *reinterpret_cast<const int2 *>(&rq[1].key);
                 if (early) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
                 if (SW) {
-                    const Real ray = mul_(rq->pa[0], sigma);        // :313-316
+                    const Real ray = mul_(rq->w[0], sigma);         // :313-316 (moles_per_layer == simple_weight, same product)
                     tau = add_(tau, ray);                           // :456
                     val[0][q] = tau;
                     val[1][q] = div_fast(ray, tau);                 // :459
                 } else {
-                    Real p0, p1, p2, p3;
-                    lds4<Real>(rq->pa, p0, p1, p2, p3);
-                    const float *pl = wpl + ix.z, *pv = wpl + ix.w;
-                    const Real lev_next = fma_(p3, (Real)pv[kGP], mul_(p2, (Real)pv[0]));
                     val[0][q] = tau;
-                    val[1 % NOUT][q] = fma_(p1, (Real)pl[kGP], mul_(p0, (Real)pl[0]));
-                    val[2 % NOUT][q] = lev_next;        // lev_source_inc(:,j) = B(tlev(j+1))  :423
-                    val[3 % NOUT][q] = lev_prev[q];     // lev_source_dec(:,j) = B(tlev(j))    :424
-                    lev_prev[q] = lev_next;
                 }
                 rp[q] = rq + 1;
             }
@@ -681,19 +744,12 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         }
     }
 
-    // ---- per-column 2-D outputs -------------------------------------------------
+    // ---- per-column 2-D output (SW; the LW surface source is written by the Planck warps) ----------
+    if (SW) {
 #pragma unroll
-    for (int q = 0; q < CPW; ++q) {
-        if (col0 + warp * CPW + q < ncol && g0 + lane < ngpt && a.out2d) {
-            if (SW) {
+        for (int q = 0; q < CPW; ++q)
+            if (col0 + warp * CPW + q < ncol && g0 + lane < ngpt && a.out2d)
                 a.out2d[col[q] + (long long)ncol * g] = (Real)m.solar[g];                                  // :468-472
-            } else {
-                double a0, a1;
-                const int it = planck_index(m, (double)a.tsfc[col[q]], a0, a1);                            // :408-412
-                const float *p = wpl + (max(it, 1) - 1) * kGP;
-                a.out2d[col[q] + (long long)ncol * g] = fma_((Real)__ddiv_rn(a1, m.pi), (Real)p[kGP], mul_((Real)__ddiv_rn(a0, m.pi), (Real)p[0]));
-            }
-        }
     }
 }
 
@@ -753,21 +809,22 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
                                  const TmaMaps *maps = nullptr)
 {
-    constexpr int NOUT = SW ? 2 : 4;
+    constexpr int NOUT = SW ? 2 : 1;
+    constexpr int NPW = SW ? 0 : NPW_LW;  // Planck warps (longwave only)
     constexpr int TCP = TMA ? TC : TC + 1;
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
                         ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
-                        (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float) * m.nplanck * kGP);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW>;
+                        (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
     static const TmaMaps no_maps{};
-    kern<<<grid, (TC / CPW + NI + NWW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
+    kern<<<grid, (TC / CPW + NI + NWW + NPW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
     return cudaGetLastError();
 }
 
@@ -795,54 +852,34 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
         if (e != cudaSuccess) return e;
     }
     if (cg.nvar <= 1) {
-#ifdef ECCKD_TUNE
-        static const int variant = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
-        switch (variant) {   // NB, TC, L, NBUF, NI, NWW
-            case 1: return launch_walk_t<Real, SW, 2, 16, 2, 2, 8, 2>(m, cg, a, mix, s);
-            case 2: return launch_walk_t<Real, SW, 2, 16, 2, 2, 2, 2>(m, cg, a, mix, s);
-            case 3: return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 2>(m, cg, a, mix, s);
-            case 4: return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 4>(m, cg, a, mix, s);
-            case 5: return launch_walk_t<Real, SW, 2, 16, 1, 3, 4, 2>(m, cg, a, mix, s);
-            default: break;
-        }
-#endif
         if constexpr (sizeof(Real) == 8) {
             static const bool no_tma = getenv("ECCKD_NO_TMA") != nullptr;
             if (!no_tma && tma_eligible(a)) {
                 // staging tiles leave the SM through cp.async.bulk.tensor: no writer warps, one tile per layer
                 TmaMaps maps{};
                 bool ok = true;
-                for (int o = 0; o < (SW ? 3 : 4); ++o)
+                for (int o = 0; o < (SW ? 3 : 1); ++o)
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
 #ifdef ECCKD_TUNE
-                    static const int ni = getenv("ECCKD_NI") ? atoi(getenv("ECCKD_NI")) : 4;
-                    if (ni == 2) {
-                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 2, 1, true, 1>(m, cg, a, mix, s, &maps);
-                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 2, 1, true, 1>(m, cg, a, mix, s, &maps);
-                    }
-                    if (ni == 8) {
-                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
-                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
-                    }
-                    static const int cpw = getenv("ECCKD_CPW") ? atoi(getenv("ECCKD_CPW")) : 1;
-                    if (cpw == 2) {
-                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 2>(m, cg, a, mix, s, &maps);
-                        else return launch_walk_t<Real, SW, 2, 16, 1, 5, 4, 1, true, 2>(m, cg, a, mix, s, &maps);
+                    static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+                    if constexpr (!SW) {
+                        if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
+                        if (v == 3) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 11>(m, cg, a, mix, s, &maps);
+                        if (v == 5) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 6>(m, cg, a, mix, s, &maps);
                     }
 #endif
-                    // one column per compute warp (16 warps): measured faster than two columns x 8 warps (ECCKD_CPW=2 in tuning builds)
-                    // LW records carry the Planck indices too (two more IEEE divisions per level): 8 index warps keep ahead
+                    // one column per compute warp (16 warps): measured faster than two columns x 8 warps
                     if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 5, 8, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
                 }
             }
         }
-        // writer-warp path.  LW keeps its Planck LUT in shared memory next to the records: room for 2 staging tiles; SW for 4
+        // writer-warp path (fp32, odd ncol, unaligned outputs)
         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
-        else return launch_walk_t<Real, SW, 2, 16, 2, 2, 4, 4>(m, cg, a, mix, s);
+        else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
     }
-    return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1>(m, cg, a, mix, s);
+    return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1, false, 1, 4>(m, cg, a, mix, s);
 }
 
 template <typename Real, bool SW>
