@@ -303,7 +303,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 {
     constexpr int NOUT = SW ? 2 : 1;      // staged outputs: tau (+ ssa).  SW's g plane is zero-filled by the store warp;
                                           // LW's three Planck sources are written by the Planck warps, straight to global memory
-    static_assert(SW ? NPW == 0 : NPW >= 1, "longwave needs Planck warps, shortwave has none");
+    static_assert(SW || NPW >= 1, "longwave needs Planck warps");
+    constexpr bool ZERO_BY_WARP = SW && NPW >= 1;   // SW: helper warps write the g = 0 plane with plain full-line stores
     // writer-warp path: padded column stride (conflict-free transpose both ways).
     // TMA path: dense 128-byte rows [g][column] in the 128B-swizzle pattern the tensor map expects.
     constexpr int TCP = TMA ? TC : TC + 1;
@@ -373,7 +374,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o)
                     if (a.out[o]) tma_store_3d(&maps.m[o], sb + o * ROWS, (int)col0, n, g0);
-                if (SW && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, (int)col0, n, g0);     // g = 0  :460
+                if (SW && !ZERO_BY_WARP && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, (int)col0, n, g0);     // g = 0  :460
                 tma_commit();
                 tma_wait_read<0>();                     // the tile has been read out of shared memory: hand it back
                 mbar_arrive(&bar_empty[b]);
@@ -415,7 +416,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                             for (int l2 = 0; l2 < L; ++l2)
                                 if (a.out[o] && l2 < nl) store_cs(reinterpret_cast<Real *>(dst + pitch * l2), v[o * L + l2]);
                         }
-                        if (SW && a.out[2]) {
+                        if (SW && !ZERO_BY_WARP && a.out[2]) {
                             char *dst = reinterpret_cast<char *>(a.out[2]) + off;
 #pragma unroll
                             for (int l2 = 0; l2 < L; ++l2)
@@ -426,6 +427,23 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);
+        }
+        return;
+    }
+
+    // =========================== zero-plane warps (SW) ===========================
+    if (SW && NPW >= 1 && warp >= NCW + NI + NWW) {
+        constexpr int LPU = 32 / TC;
+        const int pw = warp - (NCW + NI + NWW);
+        const int c = lane % TC, lsel = lane / TC;
+        const int ng = min(kGP, ngpt - g0);
+        if (a.out[2] && col0 + c < ncol) {
+            const unsigned plane32 = (unsigned)((long long)ncol * nlay);
+            for (int j = pw * LPU + lsel; j < nlay; j += NPW * LPU) {
+                unsigned off = (unsigned)(col0 + c + (long long)ncol * j) + plane32 * (unsigned)g0;
+#pragma unroll 4
+                for (int gq = 0; gq < ng; ++gq, off += plane32) store_cs(a.out[2] + off, (Real)0);     // g = 0  :460
+            }
         }
         return;
     }
@@ -809,12 +827,12 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
                                  const TmaMaps *maps = nullptr)
 {
     constexpr int NOUT = SW ? 2 : 1;
-    constexpr int NPW = SW ? 0 : NPW_LW;  // Planck warps (longwave only)
+    constexpr int NPW = SW ? NPW_SW : NPW_LW;  // helper warps: Planck sources (LW) / zero g-plane (SW)
     constexpr int TCP = TMA ? TC : TC + 1;
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
                         ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
@@ -863,6 +881,10 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                 if (ok) {
 #ifdef ECCKD_TUNE
                     static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+                    if constexpr (SW) {
+                        if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 1>(m, cg, a, mix, s, &maps);
+                        if (v == 2) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 2>(m, cg, a, mix, s, &maps);
+                    }
                     if constexpr (!SW) {
                         if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
                         if (v == 3) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 11>(m, cg, a, mix, s, &maps);
