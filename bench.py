@@ -293,6 +293,32 @@ def main() -> None:
                    "ms_per_launch": sw_ms}
     launches = args.steps * nblk * 4          # per block: LW mix + LW walk + SW mix + SW walk
 
+    # ---- extras (not part of the headline): the fp32 variant on one launch-sized block ------------------
+    extras = {}
+    try:
+        atm32 = blocks[0][0].astype(torch.float32)
+        g32 = ecckd_b200.PreparedGases(atm32.gas_list(), atm32.ncol, NLAY, np.float32, dev)
+        o_lw = o_sw = None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for rep in range(4):
+            if rep == 3:
+                ev[0].record()
+            o_lw = lw.gas_optics(None, atm32.plev, atm32.tlay, atm32.tsfc, g32, tlev=atm32.tlev, out=o_lw)
+            if rep == 3:
+                ev[1].record()
+            o_sw = sw.gas_optics(None, atm32.plev, atm32.tlay, None, g32, out=o_sw)
+            if rep == 3:
+                ev[2].record()
+        torch.cuda.synchronize()
+        t_lw, t_sw = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        extras["f32"] = {"columns": atm32.ncol, "lw_ms": t_lw, "sw_ms": t_sw,
+                         "gptl_per_s": atm32.ncol * NLAY * (NG_LW + NG_SW) / ((t_lw + t_sw) * 1e-3),
+                         "lw_frac_of_hbm": algorithmic_bytes(atm32.ncol, NLAY, NG_LW, True, 4) / (t_lw * 1e-3) / 1e9 / peak,
+                         "sw_frac_of_hbm": algorithmic_bytes(atm32.ncol, NLAY, NG_SW, False, 4) / (t_sw * 1e-3) / 1e9 / peak}
+        del atm32, g32, o_lw, o_sw
+    except Exception as exc:   # extras must never break the headline line
+        extras["f32_error"] = str(exc)
+
     # free the device-resident workload before the host-array measurement
     del blocks, ring
     torch.cuda.empty_cache()
@@ -364,7 +390,7 @@ def main() -> None:
                        "l2": "every launch streams >9 GB of outputs and 0.36 GB of inputs: far larger than the 126 MB L2, no flush needed",
                        "gases": "h2o, o3 (ncol,nlay) fields; co2, ch4, n2o, o2, cfc11, cfc12 scalars (RFMIP convention)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_sw": roofline_sw,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "extras": extras,
             "split": {"lw_gptl_per_s_per_gpu": B * NLAY * NG_LW / (lw_ms * 1e-3), "sw_gptl_per_s_per_gpu": B * NLAY * NG_SW / (sw_ms * 1e-3)},
         }
         print(json.dumps(line))
