@@ -473,7 +473,8 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
             if (sidx < 0) { sidx = nslot++; slot_off.push_back(M->table_off[i]); }
             M->slot[i] = sidx;
         }
-        M->walk_model = M->tables_nonneg && M->fp32_exact && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP;
+        M->walk_model = M->tables_nonneg && M->fp32_exact && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP &&
+                        M->nplanck <= 256;   // the per-block shared-memory copy of the Planck LUT must fit beside records and tiles
         if (M->walk_model) {
             const int ngroups = (t->ngpt + kGP - 1) / kGP, ng = t->ngpt, np = t->npress, nt = t->ntemp;
             const int nvl = lut_gas >= 0 ? M->nv[lut_gas] : 0;
