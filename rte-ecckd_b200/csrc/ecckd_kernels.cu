@@ -590,16 +590,17 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // lane, and the pair of values goes to the staging tile as one conflict-free 16-byte store)
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
     const int ngroups = gridDim.y;
-    // The file tables are exact in fp32: the LUT gas and the varying gases are cached as fp32 rows (half the L1
-    // wavefronts of an fp64 row) and widened in the FMA chain (F2F has its own pipe); only the per-call mixed
-    // table, a sum of products, needs the full Real width.
+    // The file tables are exact in fp32.  The varying gases are cached as fp32 rows and widened in the FMA chain; the
+    // LUT gas (eight values per layer) is cached at full width, because the conversion pipe (16 lanes/clk/SM) is
+    // shared with the Planck warps and eight more F2F per layer measurably slow both; the per-call mixed table, a
+    // sum of products, needs the full Real width anyway.
     const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + lane;
-    const float *wlut = m.wlut32 + (size_t)grp * m.nv_lut * kSlab + lane;
+    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
     const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
 
     Real km[CPW][4];                               // slot 0: mixed table
     float kb[CPW][NB > 1 ? NB - 1 : 1][4];         // slots 1..NB-1: varying gases
-    float kh[CPW][8];
+    Real kh[CPW][8];                               // LUT gas rows at full width: keeps eight F2F per layer off the conversion pipe
     int cur_pk[CPW], cur_hk[CPW];
     long long col[CPW];
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
@@ -637,7 +638,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         }
         cur_pk[q] = pkoff;
         if (has_lut && hkoff != cur_hk[q]) {
-            const float *k = wlut + hkoff;
+            const Real *k = wlut + hkoff;
             ldg_if(kh[q][0], k + kC00, true); ldg_if(kh[q][1], k + kC10, true); ldg_if(kh[q][2], k + kC01, true); ldg_if(kh[q][3], k + kC11, true);
             ldg_if(kh[q][4], k + kSlab + kC00, true); ldg_if(kh[q][5], k + kSlab + kC10, true);
             ldg_if(kh[q][6], k + kSlab + kC01, true); ldg_if(kh[q][7], k + kSlab + kC11, true);
