@@ -359,3 +359,21 @@ def test_downstream_fluxes_within_0p01_wm2(dtype, dev, gpu_models, ck_models, c_
     sg, sr = f(out), f(ref)
     assert 500 < sr[1][:, -1].mean() < 820                                           # surface insolation at mu0 = 0.6
     assert max(np.abs(a - b).max() for a, b in zip(sg, sr)) < 0.01
+
+
+def test_in_process_multi_device_host_sharding(dev):
+    """A model replicated on every visible GPU: the host entry points shard the columns over the devices (no
+    collective) and reproduce the single-device result bitwise.  Needs >= 2 GPUs (verified on a 2-GPU box with
+    tools/multidev_host_check.py); skipped on the single-GPU test box."""
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("single GPU")
+    plev, tlay, tlev, tsfc, gases = atm_numpy(synthetic.make_atmosphere(333, 60))
+    for key in ("lw_fsck", "sw_wide"):
+        one = ecckd_b200.GasOpticsEcckd.load(FILES[key], devices=[0])
+        many = ecckd_b200.GasOpticsEcckd.load(FILES[key], devices=list(range(ndev)))
+        lw = one.source_is_internal()
+        a = one.gas_optics(None, plev, tlay, tsfc if lw else None, gases, tlev=tlev if lw else None)
+        b = many.gas_optics(None, plev, tlay, tsfc if lw else None, gases, tlev=tlev if lw else None, block_cols=50)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (key, k)
