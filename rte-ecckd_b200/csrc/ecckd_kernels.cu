@@ -231,6 +231,13 @@ __device__ __forceinline__ Real bil4(Real c0, Real c1, Real c2, Real c3, K k0, K
 // corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
 constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
 
+// experiment switches of the tuning build (ECCKD_DBG environment variable); compiled out of the production library
+#ifdef ECCKD_TUNE
+#define ECCKD_DBG(bit) ((a.dbg & (bit)) != 0)
+#else
+#define ECCKD_DBG(bit) false
+#endif
+
 // ---- mbarrier helpers (shared::cta, generic proxy only) -------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -250,6 +257,41 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)   // non-blocking probe (acquire.cta)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Make a loop-invariant value opaque to the optimiser, so that it is kept in a register instead of being
+// rematerialised from kernel parameters and special registers in every iteration of the layer loop.
+template <typename T> __device__ __forceinline__ void keep(const T *&p) { asm volatile("" : "+l"(p)); }
+__device__ __forceinline__ void keep(int &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep(unsigned &v) { asm volatile("" : "+r"(v)); }
+// the same barrier operations on a precomputed shared-window address (saves the generic -> shared conversion per use)
+__device__ __forceinline__ void mbar_arrive_a(unsigned addr)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_a(unsigned addr, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // ---- TMA (cp.async.bulk.tensor) store helpers ------------------------------------
@@ -276,6 +318,16 @@ __device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "+f"(dst) : "l"(p), "r"((int)pred));
 }
 
+// predicated streaming store (keeps the Planck g-loop free of divergent branches)
+__device__ __forceinline__ void stcs_if(double *p, double v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)pred) : "memory");
+}
+
 // ============================================================================
 // walk_kernel: a three-role, warp-specialised pipeline inside one block
 //
@@ -295,8 +347,11 @@ __device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
 // chunks, compute -> writer through NBUF tiles of L layers.
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
+// RF = flavour of the compute warps' cache refill, a bit set tuned per band on B200:
+//   1 branch-free refill (all loads predicated)      2 loop invariants pinned in registers
+//   4 tile-free barrier probed before the arithmetic  8 refill issued after the staging fence ("late")
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7>
 __global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -329,7 +384,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // Roles are laid out in LOGICAL warp order [compute | index | store | Planck]; hardware warp ids run the other way
     // round because the SM's issue arbiter prefers the highest warp id: the latency-bound compute warps get priority
     // over the throughput-oriented Planck warps.
-    constexpr int NWARPS = TC / CPW + NI + NWW + NPW;
+    constexpr int HB = NCW + NI + NWW;              // first helper (Planck / zero-plane) warp
+    constexpr int NWARPS = HB + NPW;
     const int warp = NWARPS - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
     const long long col0 = (long long)blockIdx.x * TC;
@@ -363,9 +419,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     __syncthreads();
     const int nround = (nlay + 31) / 32;
 
-    if ((a.dbg & 128) && warp < NCW + NI + NWW) return;   // experiment: Planck warps only
+    if (ECCKD_DBG(128) && warp < HB) return;   // experiment: Planck warps only
     // =========================== TMA store warp ==================================
-    if (TMA && warp >= NCW + NI && warp < NCW + NI + NWW) {
+    if (TMA && warp >= NCW + NI && warp < HB) {
         if (lane == 0) {
             for (int n = 0; n < nlay; ++n) {            // one tile per layer
                 const int b = n % NBUF;
@@ -400,7 +456,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             mbar_wait(&bar_full[b], u & 1);
             const Real *sb = stage + (size_t)b * TILE + c;
             const long long off0 = ((col0 + c) + (long long)ncol * lay0) * (long long)sizeof(Real) + plane * (g0 + gsub);
-            if (c_ok && !(a.dbg & 1)) {
+            if (c_ok && !ECCKD_DBG(1)) {
 #pragma unroll 2
                 for (int gi = 0; gi < 32 / GSTEP; ++gi) {
                     const int gg = gsub + gi * GSTEP;
@@ -432,9 +488,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== zero-plane warps (SW) ===========================
-    if (SW && NPW >= 1 && warp >= NCW + NI + NWW) {
+    if (SW && NPW >= 1 && warp >= HB) {
         constexpr int LPU = 32 / TC;
-        const int pw = warp - (NCW + NI + NWW);
+        const int pw = warp - HB;
         const int c = lane % TC, lsel = lane / TC;
         const int ng = min(kGP, ngpt - g0);
         if (a.out[2] && col0 + c < ncol) {
@@ -449,15 +505,15 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== Planck warps (LW) ===============================
-    // lanes = (column, layer): a unit is TC columns x 32/TC layers.  Per g-point every lane interpolates its own
+    // lanes = (column, level): a unit is TC columns x 32/TC levels.  Per g-point every lane interpolates its own
     // rows of the shared-memory LUT and the warp stores full 128-byte column runs of lay_source,
     // lev_source_inc and lev_source_dec directly -- these three outputs (75 % of the longwave bytes) never
-    // touch the staging tiles.  inc(:,j) and dec(:,j+1) are the same expression of the same level
-    // temperature, hence bitwise equal, as when the reference copies one buffer twice (:423-424).
-    if (!SW && warp >= NCW + NI + NWW) {
-        if (a.dbg & 64) return;
-        constexpr int LPU = 32 / TC;                  // layers per unit
-        const int pw = warp - (NCW + NI + NWW);
+    // touch the staging tiles.  lev_source_inc(:,j-1) and lev_source_dec(:,j) are both B(tlev(:,j)) (:423-424):
+    // the lane of level j evaluates it once and stores it twice, so a cell costs two Planck evaluations, not three.
+    if (!SW && warp >= HB) {
+        if (ECCKD_DBG(64)) return;
+        constexpr int LPU = 32 / TC;                  // levels per unit
+        const int pw = warp - HB;
         const int c = lane % TC, lsel = lane / TC;
         const bool c_ok = col0 + c < ncol;
         const long long colp = min(col0 + c, (long long)ncol - 1);
@@ -465,52 +521,51 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         const int S = m.nplanck;
         const long long plane = (long long)ncol * nlay;          // elements between g-points
         const bool has_lev = a.tlev != nullptr;
+        const int nunit_lim = has_lev ? nlay + 1 : nlay;         // levels 0..nlay carry a value when tlev is present
         // software pipeline: the temperatures of the next unit are fetched before the g-loop of the current one
-        auto fetch = [&](int u, double &tl, double &tu, double &td) {
-            const int jj = min(u * LPU + lsel, nlay - 1);
-            tl = (double)a.tlay[colp + (long long)ncol * jj];
-            tu = td = 0.0;
-            if (has_lev) { tu = (double)a.tlev[colp + (long long)ncol * jj]; td = (double)a.tlev[colp + (long long)ncol * (jj + 1)]; }
-        };
-        double tl_n, tu_n, td_n;
-        if (pw * LPU < nlay) fetch(pw, tl_n, tu_n, td_n);
-        const unsigned plane32 = (unsigned)plane;            // elements between g-points (the walking kernel needs ncol*nlay*ngpt < 2^31)
-        for (int u = pw; u * LPU < nlay; u += NPW) {
+        auto fetch = [&](int u, double &tl, double &tv) {
             const int j = u * LPU + lsel;
-            const bool ok = c_ok && j < nlay;
-            const int jj = min(j, nlay - 1);
-            const double tl = tl_n, tu = tu_n, td = td_n;
-            if ((u + NPW) * LPU < nlay) fetch(u + NPW, tl_n, tu_n, td_n);
+            tl = (double)a.tlay[colp + (long long)ncol * min(j, nlay - 1)];
+            tv = 0.0;
+            if (has_lev) tv = (double)a.tlev[colp + (long long)ncol * min(j, nlay)];
+        };
+        double tl_n, tv_n;
+        if (pw * LPU < nunit_lim) fetch(pw, tl_n, tv_n);
+        const unsigned plane32 = (unsigned)plane;            // elements between g-points (the walking kernel needs ncol*nlay*ngpt < 2^31)
+        const Real *o_lay = a.out[1], *o_inc = a.out[2], *o_dec = a.out[3];
+        keep(o_lay); keep(o_inc); keep(o_dec);
+        const float2 *spl2 = reinterpret_cast<const float2 *>(spl);
+        for (int u = pw; u * LPU < nunit_lim; u += NPW) {
+            const int j = u * LPU + lsel;
+            const bool ok_lay = c_ok && j < nlay;                       // lay_source(:,j), lev_source_dec(:,j)
+            const bool ok_inc = c_ok && has_lev && j >= 1 && j <= nlay; // lev_source_inc(:,j-1)
+            const double tl = tl_n, tv = tv_n;
+            if ((u + NPW) * LPU < nunit_lim) fetch(u + NPW, tl_n, tv_n);
             double a0, a1;
             int it = planck_index(m, tl, a0, a1);
-            const float2 *tl_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
+            const float2 *tl_p = spl2 + (max(it, 1) - 1);
             const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
-            const unsigned o = (unsigned)(colp + (long long)ncol * jj) + plane32 * (unsigned)g0;
+            unsigned off = (unsigned)colp + (unsigned)ncol * (unsigned)j + plane32 * (unsigned)g0;
+            int so = 0;
             if (has_lev) {
-                it = planck_index(m, tu, a0, a1);
-                const float2 *tu_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
-                const Real u0 = (Real)__ddiv_rn(a0, m.pi), u1 = (Real)__ddiv_rn(a1, m.pi);
-                it = planck_index(m, td, a0, a1);
-                const float2 *td_p = reinterpret_cast<const float2 *>(spl) + (max(it, 1) - 1);
-                const Real d0 = (Real)__ddiv_rn(a0, m.pi), d1 = (Real)__ddiv_rn(a1, m.pi);
-                unsigned off = o;
-                int so = 0;
+                it = planck_index(m, tv, a0, a1);
+                const float2 *tv_p = spl2 + (max(it, 1) - 1);
+                const Real v0 = (Real)__ddiv_rn(a0, m.pi), v1 = (Real)__ddiv_rn(a1, m.pi);
 #pragma unroll 4
                 for (int gq = 0; gq < ng; ++gq, off += plane32, so += S) {
-                    const float2 pl = tl_p[so], pd = td_p[so], pu = tu_p[so];
+                    const float2 pl = tl_p[so], pv = tv_p[so];
                     const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
-                    const Real vi = fma_(d1, (Real)pd.y, mul_(d0, (Real)pd.x));      // lev_source_inc(:,j) = B(tlev(j+1))  :423
-                    const Real vd = fma_(u1, (Real)pu.y, mul_(u0, (Real)pu.x));      // lev_source_dec(:,j) = B(tlev(j))    :424
-                    if (ok) { store_cs(a.out[1] + off, vl); store_cs(a.out[2] + off, vi); store_cs(a.out[3] + off, vd); }
+                    const Real vv = fma_(v1, (Real)pv.y, mul_(v0, (Real)pv.x));      // B(tlev(:,j))
+                    stcs_if(const_cast<Real *>(o_lay) + off, vl, ok_lay);
+                    stcs_if(const_cast<Real *>(o_dec) + off, vv, ok_lay);                        // lev_source_dec(:,j)   :424
+                    stcs_if(const_cast<Real *>(o_inc) + (off - (unsigned)ncol), vv, ok_inc);      // lev_source_inc(:,j-1) :423
                 }
             } else {
-                unsigned off = o;
-                int so = 0;
 #pragma unroll 4
                 for (int gq = 0; gq < ng; ++gq, off += plane32, so += S) {
                     const float2 pl = tl_p[so];
                     const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
-                    if (ok) store_cs(a.out[1] + off, vl);
+                    stcs_if(const_cast<Real *>(o_lay) + off, vl, ok_lay);
                 }
             }
         }
@@ -537,7 +592,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             for (int cs = iw; cs < TC; cs += NI) {
                 const long long col = min(col0 + cs, (long long)ncol - 1);   // tail tiles recompute the last column; never stored
                 RecT rec;
-                if (j < nlay && !((a.dbg & 2) && r > 0)) {
+                if (j < nlay && !(ECCKD_DBG(2) && r > 0)) {
                     const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
                     const double tl = (double)a.tlay[col + (long long)ncol * j];
                     const CellIndex ci = cell_index(m, pu, pl, tl);
@@ -577,7 +632,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     rec.pad0 = rec.pad1 = 0;
                 }
                 if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
-                if (j < nlay && !((a.dbg & 2) && r > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
+                if (j < nlay && !(ECCKD_DBG(2) && r > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rec_full[rb * TC + cs]);
             }
@@ -597,6 +652,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + lane;
     const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
     const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
+    const float *wvar = wbil + (NB == 2 ? cg.var_off[0] : 0);       // NB == 2: the one varying gas
+    if constexpr ((RF & 2) != 0) { keep(wvar); keep(wlut); keep(wmix); }
 
     Real km[CPW][4];                               // slot 0: mixed table
     float kb[CPW][NB > 1 ? NB - 1 : 1][4];         // slots 1..NB-1: varying gases
@@ -615,34 +672,37 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         col[q] = min(col0 + warp * CPW + q, (long long)ncol - 1);
     }
 
-    // (re)load the register cache of column q for corner offsets (pkoff, hkoff); no-ops when unchanged
+    // (re)load the register cache of column q for corner offsets (pkoff, hkoff); no-ops when unchanged.
+    // All addresses are formed before the first load issues, so that the look-up-table rows never queue behind the
+    // scoreboard of the bilinear rows (measured: a false dependency through a reused address register cost one L2
+    // round trip per pressure-row change).  RF & 1: branch-free (every load predicated).
     auto refill = [&](int q, int pkoff, int hkoff) {
         const bool changed = pkoff != cur_pk[q];
         const bool shift = pkoff == cur_pk[q] + kNTP * kGP;      // ip0 advanced by one, it0 unchanged
         const bool full = changed && !shift;
-        if (changed) {
-            {
-                const Real *k = wmix + pkoff;
-                if (shift) { km[q][0] = km[q][1]; km[q][2] = km[q][3]; }
-                ldg_if(km[q][0], k + kC00, full && has_mix); ldg_if(km[q][2], k + kC01, full && has_mix);
-                ldg_if(km[q][1], k + kC10, has_mix); ldg_if(km[q][3], k + kC11, has_mix);
-            }
+        const bool hch = has_lut && hkoff != cur_hk[q];
+        const Real *kmp = wmix + pkoff;
+        const Real *khp = wlut + hkoff;
+        keep(kmp); keep(khp);
+        if ((RF & 1) || changed) {
+            if (shift) { km[q][0] = km[q][1]; km[q][2] = km[q][3]; }
+            ldg_if(km[q][0], kmp + kC00, full && has_mix); ldg_if(km[q][2], kmp + kC01, full && has_mix);
+            ldg_if(km[q][1], kmp + kC10, changed && has_mix); ldg_if(km[q][3], kmp + kC11, changed && has_mix);
 #pragma unroll
             for (int s = 0; s < NB - 1; ++s) {
                 const bool on = s < nvar;
-                const float *k = wbil + cg.var_off[s] + pkoff;
+                const float *k = (NB == 2 ? wvar : wbil + cg.var_off[s]) + pkoff;
                 if (shift) { kb[q][s][0] = kb[q][s][1]; kb[q][s][2] = kb[q][s][3]; }
                 ldg_if(kb[q][s][0], k + kC00, full && on); ldg_if(kb[q][s][2], k + kC01, full && on);
-                ldg_if(kb[q][s][1], k + kC10, on); ldg_if(kb[q][s][3], k + kC11, on);
+                ldg_if(kb[q][s][1], k + kC10, changed && on); ldg_if(kb[q][s][3], k + kC11, changed && on);
             }
         }
-        cur_pk[q] = pkoff;
-        if (has_lut && hkoff != cur_hk[q]) {
-            const Real *k = wlut + hkoff;
-            ldg_if(kh[q][0], k + kC00, true); ldg_if(kh[q][1], k + kC10, true); ldg_if(kh[q][2], k + kC01, true); ldg_if(kh[q][3], k + kC11, true);
-            ldg_if(kh[q][4], k + kSlab + kC00, true); ldg_if(kh[q][5], k + kSlab + kC10, true);
-            ldg_if(kh[q][6], k + kSlab + kC01, true); ldg_if(kh[q][7], k + kSlab + kC11, true);
+        if ((RF & 1) || hch) {
+            ldg_if(kh[q][0], khp + kC00, hch); ldg_if(kh[q][1], khp + kC10, hch); ldg_if(kh[q][2], khp + kC01, hch); ldg_if(kh[q][3], khp + kC11, hch);
+            ldg_if(kh[q][4], khp + kSlab + kC00, hch); ldg_if(kh[q][5], khp + kSlab + kC10, hch);
+            ldg_if(kh[q][6], khp + kSlab + kC01, hch); ldg_if(kh[q][7], khp + kSlab + kC11, hch);
         }
+        cur_pk[q] = pkoff;
         cur_hk[q] = hkoff;
     };
 
@@ -653,6 +713,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                            : stage + lane * TC + ((((warp >> 1) ^ (lane & 7)) << 1) | (warp & 1));
     else st = stage + lane * TCP + warp;
     int ls = 0, b = 0, fill = 0;               // layer inside the tile, ring slot, fills of slot 0 so far
+    unsigned a_full = smem_u32(bar_full), a_empty = smem_u32(bar_empty);   // shared-window addresses, kept in registers
+    int lane_k = lane;
+    if constexpr ((RF & 2) != 0) { keep(a_full); keep(a_empty); keep(lane_k); }
     for (int r = 0; r < nround; ++r) {
         const int rb = r & 1;
         const int len = min(32, nlay - r * 32);
@@ -665,10 +728,15 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             refill(q, k0.x & 0xffff, k0.y);
         }
         for (int l = 0; l < len; ++l) {
-            if (ls == 0 && fill >= 1) mbar_wait(&bar_empty[b], (fill - 1) & 1);   // tile free again?
+            // tile free again?  Probe now, look at the answer only before the staging store: the barrier round
+            // trip hides under the interpolation arithmetic
+            // (parity (fill & 1) ^ 1: the first pass over the ring asks for the phase before the initial one, which
+            //  a fresh barrier reports as complete)
+            const bool need_tile = ls == 0;
+            const bool tile_ok = !need_tile || ((RF & 4) && mbar_test_a(a_empty + b * 8, (fill & 1) ^ 1));
             Real val[NOUT][CPW];
             int2 k1[CPW];
-            constexpr bool early = !TMA || !SW;          // measured: LW prefers the early fetch, SW the late one
+            constexpr bool early = !(RF & 8);          // measured: LW prefers the early fetch, SW the late one
 #pragma unroll
             for (int q = 0; q < CPW; ++q) {
                 const RecT *rq = rp[q];
@@ -720,7 +788,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
                 k1[q] = make_int2(cur_pk[q], cur_hk[q]);
                 if (l + 1 < len) k1[q] = *reinterpret_cast<const int2 *>(&rq[1].key);
-                if (early) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
+                if (early && !ECCKD_DBG(8)) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
                 if (SW) {
                     const Real ray = mul_(rq->w[0], sigma);         // :313-316 (moles_per_layer == simple_weight, same product)
                     tau = add_(tau, ray);                           // :456
@@ -731,6 +799,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
                 rp[q] = rq + 1;
             }
+            if (!tile_ok) mbar_wait_a(a_empty + b * 8, (fill & 1) ^ 1);
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) {
                 if constexpr (CPW == 2) {
@@ -744,10 +813,10 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             if (++ls == L || (r == nround - 1 && l == len - 1)) {
                 if (TMA) fence_proxy_async_smem();     // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[b]);
+                if (lane_k == 0) mbar_arrive_a(a_full + b * 8);
                 // TMA path: the proxy fence drains this thread's outstanding loads, so the next layer's corner
                 // fetch is issued after it (it then overlaps the next record read and Planck arithmetic)
-                if (!early) {
+                if (!early && !ECCKD_DBG(8)) {
 #pragma unroll
                     for (int q = 0; q < CPW; ++q) refill(q, k1[q].x & 0xffff, k1[q].y);
                 }
@@ -828,7 +897,8 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0>
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0,
+          int RF = 7>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
                                  const TmaMaps *maps = nullptr)
 {
@@ -838,7 +908,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
                         ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
                         (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW>;
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW, RF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
@@ -882,6 +952,14 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                 if (ok) {
 #ifdef ECCKD_TUNE
                     static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+#define ECCKD_RF_CASE(rf) \
+                    if (v == 100 + rf) { \
+                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, rf>(m, cg, a, mix, s, &maps); \
+                        else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 7, 0, rf>(m, cg, a, mix, s, &maps); \
+                    }
+                    ECCKD_RF_CASE(0) ECCKD_RF_CASE(1) ECCKD_RF_CASE(2) ECCKD_RF_CASE(3) ECCKD_RF_CASE(4) ECCKD_RF_CASE(5) ECCKD_RF_CASE(6)
+                    ECCKD_RF_CASE(8) ECCKD_RF_CASE(12) ECCKD_RF_CASE(14) ECCKD_RF_CASE(15) ECCKD_RF_CASE(10)
+#undef ECCKD_RF_CASE
                     if constexpr (SW) {
                         if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 1>(m, cg, a, mix, s, &maps);
                         if (v == 2) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 2>(m, cg, a, mix, s, &maps);
@@ -890,17 +968,35 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                         if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
                         if (v == 3) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 11>(m, cg, a, mix, s, &maps);
                         if (v == 5) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 6>(m, cg, a, mix, s, &maps);
+                        if (v == 6) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 7>(m, cg, a, mix, s, &maps);
                     }
 #endif
                     // one column per compute warp (16 warps): measured faster than two columns x 8 warps
-                    if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1>(m, cg, a, mix, s, &maps);
+                    // refill flavour (RF) and Planck-warp count as measured on B200: SW prefers the branchy, late refill
+                    if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4, 0, 7>(m, cg, a, mix, s, &maps);
                 }
             }
         }
+#ifdef ECCKD_TUNE
+        if constexpr (!SW && sizeof(Real) == 8) {
+            static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+            if (v == 21) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 6>(m, cg, a, mix, s);
+            if (v == 22) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 6>(m, cg, a, mix, s);
+            if (v == 23) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 1, false, 1, 7>(m, cg, a, mix, s);
+            if (v == 24) return launch_walk_t<Real, SW, 2, 16, 4, 3, 4, 1, false, 1, 7>(m, cg, a, mix, s);
+            if (v == 11) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 2, false, 1, 8>(m, cg, a, mix, s);
+            if (v == 12) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 8>(m, cg, a, mix, s);
+            if (v == 13) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 10>(m, cg, a, mix, s);
+            if (v == 14) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 3, false, 1, 9>(m, cg, a, mix, s);
+            if (v == 15) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 10>(m, cg, a, mix, s);
+            if (v == 16) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 4, false, 1, 8>(m, cg, a, mix, s);
+            if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 4, false, 1, 8>(m, cg, a, mix, s);
+        }
+#endif
         // writer-warp path (fp32, odd ncol, unaligned outputs)
         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
-        else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
+        else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4>(m, cg, a, mix, s);
     }
     return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1, false, 1, 4>(m, cg, a, mix, s);
 }
