@@ -354,7 +354,8 @@ __device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7>
 __global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
-            const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
+            const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps,
+            const int tiles_per_chunk)
 {
     constexpr int NOUT = SW ? 2 : 1;      // staged outputs: tau (+ ssa).  SW's g plane is zero-filled by the store warp;
                                           // LW's three Planck sources are written by the Planck warps, straight to global memory
@@ -368,6 +369,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     constexpr int NCW = TC / CPW;          // compute warps
     
     static_assert(CPW == 1 || (CPW == 2 && TMA), "two columns per warp needs the 16-byte swizzled staging of the TMA path");
+    static_assert(!(RF & 8) || L == 1, "the late refill is issued at tile hand-over, i.e. once per layer only when L == 1");
     static_assert(!TMA || (L == 1 && NWW == 1 && sizeof(Real) * TC == 128), "TMA store path: one layer per tile, 128-byte rows, one store warp");
     using RecT = Rec<Real, NB>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -388,7 +390,19 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     constexpr int NWARPS = HB + NPW;
     const int warp = NWARPS - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
-    const long long col0 = (long long)blockIdx.x * TC;
+    // Persistent blocks: the columns are cut into chunks of CH tiles of TC columns (CH = 2 for large calls: the
+    // Planck warps then store 256-byte runs) and block b walks chunks b, b + gridDim.x, ...  The barriers, the Planck
+    // table in shared memory and the register caches are set up once; the index warps run ahead into the next tile
+    // while the compute warps finish the current one; and because the blocks advance through neighbouring chunks
+    // together, the stores of all SMs stay close together in memory (measured: giving each block one contiguous
+    // column range instead costs 7 %).
+    const int CH = tiles_per_chunk;
+    const int ntile_all = (ncol + TC - 1) / TC;
+    const int nchunk_all = (ntile_all + CH - 1) / CH;
+    const int nchunk = (nchunk_all - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // chunks of this block (>= 1)
+    const int nslot = nchunk * CH;                                                  // tile slots of this block
+    // tile slot -> global tile (>= ntile_all: the empty second half of the last chunk; every role skips it)
+    auto tile_of = [&](int ts) { const int k = ts / CH; return ((int)blockIdx.x + k * (int)gridDim.x) * CH + (ts - k * CH); };
     const int ngpt = m.ngpt;
     const int grp = blockIdx.y, g0 = grp * kGP;
     const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
@@ -423,17 +437,23 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // =========================== TMA store warp ==================================
     if (TMA && warp >= NCW + NI && warp < HB) {
         if (lane == 0) {
-            for (int n = 0; n < nlay; ++n) {            // one tile per layer
-                const int b = n % NBUF;
-                mbar_wait(&bar_full[b], (n / NBUF) & 1);
-                const Real *sb = stage + (size_t)b * TILE;
+            int b = 0, par = 0;                             // ring slot and its phase, running over all tiles
+            for (int ts = 0; ts < nslot; ++ts) {
+                const int gt = tile_of(ts);
+                if (gt >= ntile_all) continue;
+                const int col0 = gt * TC;
+                for (int n = 0; n < nlay; ++n) {            // one staging tile per layer
+                    mbar_wait(&bar_full[b], par);
+                    const Real *sb = stage + (size_t)b * TILE;
 #pragma unroll
-                for (int o = 0; o < NOUT; ++o)
-                    if (a.out[o]) tma_store_3d(&maps.m[o], sb + o * ROWS, (int)col0, n, g0);
-                if (SW && !ZERO_BY_WARP && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, (int)col0, n, g0);     // g = 0  :460
-                tma_commit();
-                tma_wait_read<0>();                     // the tile has been read out of shared memory: hand it back
-                mbar_arrive(&bar_empty[b]);
+                    for (int o = 0; o < NOUT; ++o)
+                        if (a.out[o]) tma_store_3d(&maps.m[o], sb + o * ROWS, col0, n, g0);
+                    if (SW && !ZERO_BY_WARP && a.out[2]) tma_store_3d(&maps.m[2], zero_tile, col0, n, g0);     // g = 0  :460
+                    tma_commit();
+                    tma_wait_read<0>();                     // the tile has been read out of shared memory: hand it back
+                    mbar_arrive(&bar_empty[b]);
+                    if (++b == NBUF) { b = 0; par ^= 1; }
+                }
             }
             tma_wait_all<0>();
         }
@@ -446,14 +466,18 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         constexpr int GSTEP = NWT / TC;               // g-points covered per pass
         const int t = (warp - (NCW + NI)) * 32 + lane;
         const int c = t % TC, gsub = t / TC;
-        const bool c_ok = col0 + c < ncol;
         const long long plane = (long long)ncol * nlay * (long long)sizeof(Real);   // bytes between g-points
         const long long pitch = (long long)ncol * (long long)sizeof(Real);          // bytes between layers
-        const int nchunk = (nlay + L - 1) / L;
-        for (int n = 0; n < nchunk; ++n) {
-            const int b = n % NBUF, u = n / NBUF;
+        const int nchunk_lay = (nlay + L - 1) / L;
+        int b = 0, par = 0;                               // ring slot and its phase, running over all tiles
+        for (int tn = 0; tn < nslot * nchunk_lay; ++tn) {
+            const int n = tn % nchunk_lay;
+            const int gt = tile_of(tn / nchunk_lay);
+            if (gt >= ntile_all) continue;
+            const long long col0 = (long long)gt * TC;
+            const bool c_ok = col0 + c < ncol;
             const int lay0 = n * L, nl = min(L, nlay - lay0);
-            mbar_wait(&bar_full[b], u & 1);
+            mbar_wait(&bar_full[b], par);
             const Real *sb = stage + (size_t)b * TILE + c;
             const long long off0 = ((col0 + c) + (long long)ncol * lay0) * (long long)sizeof(Real) + plane * (g0 + gsub);
             if (c_ok && !ECCKD_DBG(1)) {
@@ -483,6 +507,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);
+            if (++b == NBUF) { b = 0; par ^= 1; }
         }
         return;
     }
@@ -493,54 +518,69 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         const int pw = warp - HB;
         const int c = lane % TC, lsel = lane / TC;
         const int ng = min(kGP, ngpt - g0);
-        if (a.out[2] && col0 + c < ncol) {
-            const unsigned plane32 = (unsigned)((long long)ncol * nlay);
-            for (int j = pw * LPU + lsel; j < nlay; j += NPW * LPU) {
-                unsigned off = (unsigned)(col0 + c + (long long)ncol * j) + plane32 * (unsigned)g0;
+        for (int ts = 0; ts < nslot; ++ts) {
+            const long long col0 = (long long)tile_of(ts) * TC;
+            if (a.out[2] && col0 + c < ncol) {
+                const unsigned plane32 = (unsigned)((long long)ncol * nlay);
+                for (int j = pw * LPU + lsel; j < nlay; j += NPW * LPU) {
+                    unsigned off = (unsigned)(col0 + c + (long long)ncol * j) + plane32 * (unsigned)g0;
 #pragma unroll 4
-                for (int gq = 0; gq < ng; ++gq, off += plane32) store_cs(a.out[2] + off, (Real)0);     // g = 0  :460
+                    for (int gq = 0; gq < ng; ++gq, off += plane32) store_cs(a.out[2] + off, (Real)0);     // g = 0  :460
+                }
             }
         }
         return;
     }
 
     // =========================== Planck warps (LW) ===============================
-    // lanes = (column, level): a unit is TC columns x 32/TC levels.  Per g-point every lane interpolates its own
-    // rows of the shared-memory LUT and the warp stores full 128-byte column runs of lay_source,
-    // lev_source_inc and lev_source_dec directly -- these three outputs (75 % of the longwave bytes) never
-    // touch the staging tiles.  lev_source_inc(:,j-1) and lev_source_dec(:,j) are both B(tlev(:,j)) (:423-424):
+    // lanes = (column, level).  The block's column range is cut into strips of W columns -- 32 when the block holds
+    // more than one tile (one level per unit, 256-byte store runs), else TC -- and a unit is one strip x 32/W levels.
+    // Per g-point every lane interpolates its own rows of the shared-memory LUT and the warp stores full column runs
+    // of lay_source, lev_source_inc and lev_source_dec directly: these three outputs (75 % of the longwave bytes)
+    // never touch the staging tiles.  lev_source_inc(:,j-1) and lev_source_dec(:,j) are both B(tlev(:,j)) (:423-424):
     // the lane of level j evaluates it once and stores it twice, so a cell costs two Planck evaluations, not three.
     if (!SW && warp >= HB) {
         if (ECCKD_DBG(64)) return;
-        constexpr int LPU = 32 / TC;                  // levels per unit
         const int pw = warp - HB;
-        const int c = lane % TC, lsel = lane / TC;
-        const bool c_ok = col0 + c < ncol;
-        const long long colp = min(col0 + c, (long long)ncol - 1);
+        const int W = CH * TC;                        // strip = chunk (W divides 32)
+        const int LPU = 32 / W;                       // levels per unit
+        const int c = lane % W, lsel = lane / W;
+        const int nstrip = nchunk;
         const int ng = min(kGP, ngpt - g0);
         const int S = m.nplanck;
-        const long long plane = (long long)ncol * nlay;          // elements between g-points
         const bool has_lev = a.tlev != nullptr;
-        const int nunit_lim = has_lev ? nlay + 1 : nlay;         // levels 0..nlay carry a value when tlev is present
+        const int nlevu = has_lev ? nlay + 1 : nlay;  // levels 0..nlay carry a value when tlev is present
+        const int ups = (nlevu + LPU - 1) / LPU;      // units per strip
+        const int nunit = nstrip * ups;
+        // unit u -> level j of this lane and its (clamped) column
+        auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
+            const int st = u / ups;
+            j = (u - st * ups) * LPU + lsel;
+            const long long cc = (long long)((int)blockIdx.x + st * (int)gridDim.x) * W + c;
+            c_ok = cc < ncol;
+            colp = min(cc, (long long)ncol - 1);
+        };
         // software pipeline: the temperatures of the next unit are fetched before the g-loop of the current one
         auto fetch = [&](int u, double &tl, double &tv) {
-            const int j = u * LPU + lsel;
+            int j; long long colp; bool c_ok;
+            place(u, j, colp, c_ok);
             tl = (double)a.tlay[colp + (long long)ncol * min(j, nlay - 1)];
             tv = 0.0;
             if (has_lev) tv = (double)a.tlev[colp + (long long)ncol * min(j, nlay)];
         };
         double tl_n, tv_n;
-        if (pw * LPU < nunit_lim) fetch(pw, tl_n, tv_n);
-        const unsigned plane32 = (unsigned)plane;            // elements between g-points (the walking kernel needs ncol*nlay*ngpt < 2^31)
+        if (pw < nunit) fetch(pw, tl_n, tv_n);
+        const unsigned plane32 = (unsigned)((long long)ncol * nlay);   // elements between g-points (the walking kernel needs ncol*nlay*ngpt < 2^31)
         const Real *o_lay = a.out[1], *o_inc = a.out[2], *o_dec = a.out[3];
         keep(o_lay); keep(o_inc); keep(o_dec);
         const float2 *spl2 = reinterpret_cast<const float2 *>(spl);
-        for (int u = pw; u * LPU < nunit_lim; u += NPW) {
-            const int j = u * LPU + lsel;
+        for (int u = pw; u < nunit; u += NPW) {
+            int j; long long colp; bool c_ok;
+            place(u, j, colp, c_ok);
             const bool ok_lay = c_ok && j < nlay;                       // lay_source(:,j), lev_source_dec(:,j)
             const bool ok_inc = c_ok && has_lev && j >= 1 && j <= nlay; // lev_source_inc(:,j-1)
             const double tl = tl_n, tv = tv_n;
-            if ((u + NPW) * LPU < nunit_lim) fetch(u + NPW, tl_n, tv_n);
+            if (u + NPW < nunit) fetch(u + NPW, tl_n, tv_n);
             double a0, a1;
             int it = planck_index(m, tl, a0, a1);
             const float2 *tl_p = spl2 + (max(it, 1) - 1);
@@ -569,16 +609,20 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
             }
         }
-        if (pw == 0 && a.out2d) {                      // sfc_source(:, g) = B(tsfc)   :408-412
-            double a0, a1;
-            const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
-            const int r = max(it, 1) - 1;
-            const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
-            for (int gq = lsel; gq < ng; gq += LPU)
-                if (c_ok) {
-                    const float2 ps = reinterpret_cast<const float2 *>(spl)[gq * S + r];
-                    a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, (Real)ps.y, mul_(s0, (Real)ps.x));
-                }
+        if (a.out2d) {                                 // sfc_source(:, g) = B(tsfc)   :408-412
+            for (int st = pw; st < nstrip; st += NPW) {
+                const long long cc = (long long)((int)blockIdx.x + st * (int)gridDim.x) * W + c;
+                const long long colp = min(cc, (long long)ncol - 1);
+                double a0, a1;
+                const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
+                const int r = max(it, 1) - 1;
+                const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
+                for (int gq = lsel; gq < ng; gq += LPU)
+                    if (cc < ncol) {
+                        const float2 ps = spl2[gq * S + r];
+                        a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, (Real)ps.y, mul_(s0, (Real)ps.x));
+                    }
+            }
         }
         return;
     }
@@ -586,13 +630,18 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // =========================== index warps =====================================
     if (warp >= NCW && warp < NCW + NI) {
         const int iw = warp - NCW;
-        for (int r = 0; r < nround; ++r) {
-            const int rb = r & 1, u = r >> 1;
+        int tr = 0;                                        // running round over all tiles of the block
+        for (int ts = 0; ts < nslot; ++ts) {
+          const int gt = tile_of(ts);
+          if (gt >= ntile_all) continue;
+          const long long col0 = (long long)gt * TC;
+          for (int r = 0; r < nround; ++r, ++tr) {
+            const int rb = tr & 1, u = tr >> 1;
             const int j = r * 32 + lane;
             for (int cs = iw; cs < TC; cs += NI) {
                 const long long col = min(col0 + cs, (long long)ncol - 1);   // tail tiles recompute the last column; never stored
                 RecT rec;
-                if (j < nlay && !(ECCKD_DBG(2) && r > 0)) {
+                if (j < nlay && !(ECCKD_DBG(2) && tr > 0)) {
                     const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
                     const double tl = (double)a.tlay[col + (long long)ncol * j];
                     const CellIndex ci = cell_index(m, pu, pl, tl);
@@ -632,10 +681,11 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     rec.pad0 = rec.pad1 = 0;
                 }
                 if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
-                if (j < nlay && !(ECCKD_DBG(2) && r > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
+                if (j < nlay && !(ECCKD_DBG(2) && tr > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rec_full[rb * TC + cs]);
             }
+          }
         }
         return;
     }
@@ -659,7 +709,6 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     float kb[CPW][NB > 1 ? NB - 1 : 1][4];         // slots 1..NB-1: varying gases
     Real kh[CPW][8];                               // LUT gas rows at full width: keeps eight F2F per layer off the conversion pipe
     int cur_pk[CPW], cur_hk[CPW];
-    long long col[CPW];
     const Real sigma = SW ? (Real)m.rayleigh[g] : (Real)0;
 #pragma unroll
     for (int q = 0; q < CPW; ++q) {
@@ -669,7 +718,6 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 #pragma unroll
         for (int i = 0; i < 8; ++i) kh[q][i] = 0;
         cur_pk[q] = cur_hk[q] = -0x10000;
-        col[q] = min(col0 + warp * CPW + q, (long long)ncol - 1);
     }
 
     // (re)load the register cache of column q for corner offsets (pkoff, hkoff); no-ops when unchanged.
@@ -716,13 +764,16 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     unsigned a_full = smem_u32(bar_full), a_empty = smem_u32(bar_empty);   // shared-window addresses, kept in registers
     int lane_k = lane;
     if constexpr ((RF & 2) != 0) { keep(a_full); keep(a_empty); keep(lane_k); }
-    for (int r = 0; r < nround; ++r) {
-        const int rb = r & 1;
+    int tr = 0;                                        // running round over all tiles of the block; the register
+    for (int ts = 0; ts < nslot; ++ts) {               // cache, the staging ring and the barrier phases carry over
+      if (tile_of(ts) >= ntile_all) continue;
+      for (int r = 0; r < nround; ++r, ++tr) {
+        const int rb = tr & 1;
         const int len = min(32, nlay - r * 32);
         const RecT *rp[CPW];
 #pragma unroll
         for (int q = 0; q < CPW; ++q) {
-            mbar_wait(&rec_full[rb * TC + warp * CPW + q], (r >> 1) & 1);
+            mbar_wait(&rec_full[rb * TC + warp * CPW + q], (tr >> 1) & 1);
             rp[q] = recs + (rb * TC + warp * CPW + q) * 32;
             const int2 k0 = *reinterpret_cast<const int2 *>(&rp[q]->key);
             refill(q, k0.x & 0xffff, k0.y);
@@ -830,14 +881,18 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 #pragma unroll
             for (int q = 0; q < CPW; ++q) mbar_arrive(&rec_empty[rb * TC + warp * CPW + q]);
         }
+      }
     }
 
     // ---- per-column 2-D output (SW; the LW surface source is written by the Planck warps) ----------
-    if (SW) {
+    if (SW && a.out2d && g0 + lane < ngpt) {
+        for (int ts = 0; ts < nslot; ++ts) {
 #pragma unroll
-        for (int q = 0; q < CPW; ++q)
-            if (col0 + warp * CPW + q < ncol && g0 + lane < ngpt && a.out2d)
-                a.out2d[col[q] + (long long)ncol * g] = (Real)m.solar[g];                                  // :468-472
+            for (int q = 0; q < CPW; ++q) {
+                const long long cq = (long long)tile_of(ts) * TC + warp * CPW + q;
+                if (cq < ncol) a.out2d[cq + (long long)ncol * g] = (Real)m.solar[g];                       // :468-472
+            }
+        }
     }
 }
 
@@ -897,6 +952,32 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Launch geometry of the persistent walk kernel: tiles per chunk and blocks per g-group.  One block is resident
+// per SM (shared memory); a longwave call with at least four tiles per SM uses two-tile chunks.
+static void walk_geometry(int ntile, bool sw, int &tiles_per_chunk, int &blocks)
+{
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        return n;
+    }();
+    // Two-tile chunks pay in the longwave only (wider Planck stores, measured 8 %), and only when the coarser
+    // granularity does not unbalance the blocks: compare the longest block under both choices.
+    tiles_per_chunk = 1;
+    if (!sw && ntile >= 4 * sms) {
+        const int n2 = (ntile + 1) / 2;
+        const double t1 = 1.08 * ((ntile + sms - 1) / sms), t2 = 2.0 * ((n2 + sms - 1) / sms);
+        if (t2 <= t1) tiles_per_chunk = 2;
+    }
+    int cap = sms;
+#ifdef ECCKD_TUNE
+    if (getenv("ECCKD_CH")) tiles_per_chunk = atoi(getenv("ECCKD_CH"));
+    if (getenv("ECCKD_BLOCKS")) cap = atoi(getenv("ECCKD_BLOCKS"));
+#endif
+    const int nchunk = (ntile + tiles_per_chunk - 1) / tiles_per_chunk;
+    blocks = nchunk < cap ? nchunk : cap;
+}
+
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0,
           int RF = 7>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
@@ -911,9 +992,12 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW, RF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((a.ncol + TC - 1) / TC), (unsigned)((m.ngpt + kGP - 1) / kGP));
+    const int ntile = (a.ncol + TC - 1) / TC;
+    int tpc, blocks;
+    walk_geometry(ntile, SW, tpc, blocks);
+    dim3 grid((unsigned)blocks, (unsigned)((m.ngpt + kGP - 1) / kGP));
     static const TmaMaps no_maps{};
-    kern<<<grid, (TC / CPW + NI + NWW + NPW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps);
+    kern<<<grid, (TC / CPW + NI + NWW + NPW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps, tpc);
     return cudaGetLastError();
 }
 
@@ -961,6 +1045,9 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     ECCKD_RF_CASE(8) ECCKD_RF_CASE(12) ECCKD_RF_CASE(14) ECCKD_RF_CASE(15) ECCKD_RF_CASE(10)
 #undef ECCKD_RF_CASE
                     if constexpr (SW) {
+                        if (v == 15) return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
+                        if (v == 16) return launch_walk_t<Real, SW, 2, 16, 1, 6, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
+                        if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 3, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
                         if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 1>(m, cg, a, mix, s, &maps);
                         if (v == 2) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 2>(m, cg, a, mix, s, &maps);
                     }
@@ -969,18 +1056,36 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                         if (v == 3) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 11>(m, cg, a, mix, s, &maps);
                         if (v == 5) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 6>(m, cg, a, mix, s, &maps);
                         if (v == 6) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 7>(m, cg, a, mix, s, &maps);
+                        if (v == 7) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 10) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 2>(m, cg, a, mix, s, &maps);
+                        if (v == 11) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 1>(m, cg, a, mix, s, &maps);
+                        if (v == 12) return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 15) return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 16) return launch_walk_t<Real, SW, 2, 16, 1, 6, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 18) return launch_walk_t<Real, SW, 2, 16, 1, 10, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 19) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
+                        if (v == 13) return launch_walk_t<Real, SW, 2, 16, 1, 16, 3, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
+                        if (v == 14) return launch_walk_t<Real, SW, 2, 16, 1, 16, 2, 1, true, 1, 2>(m, cg, a, mix, s, &maps);
+                        if (v == 8) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 5>(m, cg, a, mix, s, &maps);
+                        if (v == 9) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
                     }
 #endif
                     // one column per compute warp (16 warps): measured faster than two columns x 8 warps
                     // refill flavour (RF) and Planck-warp count as measured on B200: SW prefers the branchy, late refill
                     if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4, 0, 7>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, 7>(m, cg, a, mix, s, &maps);
                 }
             }
         }
 #ifdef ECCKD_TUNE
         if constexpr (!SW && sizeof(Real) == 8) {
             static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+            if (v == 31) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 3>(m, cg, a, mix, s);
+            if (v == 32) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 3>(m, cg, a, mix, s);
+            if (v == 33) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 2, false, 1, 3>(m, cg, a, mix, s);
+            if (v == 34) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 1, false, 1, 3>(m, cg, a, mix, s);
+            if (v == 35) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 3, false, 1, 3>(m, cg, a, mix, s);
             if (v == 21) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 6>(m, cg, a, mix, s);
             if (v == 22) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 6>(m, cg, a, mix, s);
             if (v == 23) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 1, false, 1, 7>(m, cg, a, mix, s);
@@ -995,7 +1100,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
         }
 #endif
         // writer-warp path (fp32, odd ncol, unaligned outputs)
-        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4>(m, cg, a, mix, s);
+        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 8, 0, 6>(m, cg, a, mix, s);
         else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4>(m, cg, a, mix, s);
     }
     return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1, false, 1, 4>(m, cg, a, mix, s);
