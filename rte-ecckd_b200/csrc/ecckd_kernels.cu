@@ -746,9 +746,14 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
         }
         if ((RF & 1) || hch) {
-            ldg_if(kh[q][0], khp + kC00, hch); ldg_if(kh[q][1], khp + kC10, hch); ldg_if(kh[q][2], khp + kC01, hch); ldg_if(kh[q][3], khp + kC11, hch);
-            ldg_if(kh[q][4], khp + kSlab + kC00, hch); ldg_if(kh[q][5], khp + kSlab + kC10, hch);
-            ldg_if(kh[q][6], khp + kSlab + kC01, hch); ldg_if(kh[q][7], khp + kSlab + kC11, hch);
+            // the same one-row shift for the look-up-table gas (its key moves with ip0 too): four loads instead of eight
+            const bool hshift = hkoff == cur_hk[q] + kNTP * kGP;
+            const bool hfull = hch && !hshift;
+            if (hshift) { kh[q][0] = kh[q][1]; kh[q][2] = kh[q][3]; kh[q][4] = kh[q][5]; kh[q][6] = kh[q][7]; }
+            ldg_if(kh[q][0], khp + kC00, hfull); ldg_if(kh[q][2], khp + kC01, hfull);
+            ldg_if(kh[q][4], khp + kSlab + kC00, hfull); ldg_if(kh[q][6], khp + kSlab + kC01, hfull);
+            ldg_if(kh[q][1], khp + kC10, hch); ldg_if(kh[q][3], khp + kC11, hch);
+            ldg_if(kh[q][5], khp + kSlab + kC10, hch); ldg_if(kh[q][7], khp + kSlab + kC11, hch);
         }
         cur_pk[q] = pkoff;
         cur_hk[q] = hkoff;
