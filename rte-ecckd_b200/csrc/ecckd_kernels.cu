@@ -350,6 +350,7 @@ __device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
 // RF = flavour of the compute warps' cache refill, a bit set tuned per band on B200:
 //   1 branch-free refill (all loads predicated)      2 loop invariants pinned in registers
 //   4 tile-free barrier probed before the arithmetic  8 refill issued after the staging fence ("late")
+//  16 refill issued as soon as the bilinears have read the cache, ahead of the rest of the layer's arithmetic
 // ============================================================================
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7>
 __global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW) * 32, 1)
@@ -800,6 +801,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 Real c0, c1, c2, c3;
                 lds4<Real>(rq->c, c0, c1, c2, c3);
                 const int key = ix.x;
+                k1[q] = make_int2(cur_pk[q], cur_hk[q]);
+                if (l + 1 < len) k1[q] = *reinterpret_cast<const int2 *>(&rq[1].key);
+                constexpr bool asap = (RF & 16) != 0;     // refill as soon as the bilinears have read the cache
                 Real tau = 0;
                 constexpr int kCommon = kMaskLut | (3 << kMaskShift);   // LUT gas + mixed table + one varying gas, all contributing
                 if (NB == 2 && (key & (kCommon | kMaskNeg)) == kCommon) {
@@ -811,6 +815,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     const Real b1 = bil4(c0, c1, c2, c3, kh[q][4], kh[q][5], kh[q][6], kh[q][7]);
                     const Real bm = bil4(c0, c1, c2, c3, km[q][0], km[q][1], km[q][2], km[q][3]);
                     const Real bv = bil4(c0, c1, c2, c3, kb[q][0][0], kb[q][0][1], kb[q][0][2], kb[q][0][3]);
+                    if (asap && !ECCKD_DBG(8)) refill(q, k1[q].x & 0xffff, k1[q].y);
                     tau = mul_(wl, fma_(v1, b1, mul_(add_((Real)1, -v1), b0)));
                     tau = fma_(w0, bm, tau);
                     tau = fma_(w1, bv, tau);
@@ -841,10 +846,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         const Real *k = wmix + (size_t)ngroups * kSlab + (key & 0xffff);
                         tau = fma_(rq->w[0], bil4(c0, c1, c2, c3, k[kC00], k[kC10], k[kC01], k[kC11]), tau);
                     }
+                    if (asap && !ECCKD_DBG(8)) refill(q, k1[q].x & 0xffff, k1[q].y);
                 }
-                k1[q] = make_int2(cur_pk[q], cur_hk[q]);
-                if (l + 1 < len) k1[q] = *reinterpret_cast<const int2 *>(&rq[1].key);
-                if (early && !ECCKD_DBG(8)) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
+                if (early && !asap && !ECCKD_DBG(8)) refill(q, k1[q].x & 0xffff, k1[q].y);   // cache is free: fetch the next layer's corners under the Planck / staging work
                 if (SW) {
                     const Real ray = mul_(rq->w[0], sigma);         // :313-316 (moles_per_layer == simple_weight, same product)
                     tau = add_(tau, ray);                           // :456
@@ -872,7 +876,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (lane_k == 0) mbar_arrive_a(a_full + b * 8);
                 // TMA path: the proxy fence drains this thread's outstanding loads, so the next layer's corner
                 // fetch is issued after it (it then overlaps the next record read and Planck arithmetic)
-                if (!early && !ECCKD_DBG(8)) {
+                if (!early && !(RF & 16) && !ECCKD_DBG(8)) {
 #pragma unroll
                     for (int q = 0; q < CPW; ++q) refill(q, k1[q].x & 0xffff, k1[q].y);
                 }
@@ -1044,10 +1048,10 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
 #define ECCKD_RF_CASE(rf) \
                     if (v == 100 + rf) { \
                         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, rf>(m, cg, a, mix, s, &maps); \
-                        else return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 7, 0, rf>(m, cg, a, mix, s, &maps); \
+                        else return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, rf>(m, cg, a, mix, s, &maps); \
                     }
-                    ECCKD_RF_CASE(0) ECCKD_RF_CASE(1) ECCKD_RF_CASE(2) ECCKD_RF_CASE(3) ECCKD_RF_CASE(4) ECCKD_RF_CASE(5) ECCKD_RF_CASE(6)
-                    ECCKD_RF_CASE(8) ECCKD_RF_CASE(12) ECCKD_RF_CASE(14) ECCKD_RF_CASE(15) ECCKD_RF_CASE(10)
+                    ECCKD_RF_CASE(6) ECCKD_RF_CASE(7)
+                    ECCKD_RF_CASE(14) ECCKD_RF_CASE(22) ECCKD_RF_CASE(23) ECCKD_RF_CASE(18) ECCKD_RF_CASE(19)
 #undef ECCKD_RF_CASE
                     if constexpr (SW) {
                         if (v == 15) return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
@@ -1079,13 +1083,15 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     // one column per compute warp (16 warps): measured faster than two columns x 8 warps
                     // refill flavour (RF) and Planck-warp count as measured on B200: SW prefers the branchy, late refill
                     if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
-                    else return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, 7>(m, cg, a, mix, s, &maps);
+                    else return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, 18>(m, cg, a, mix, s, &maps);
                 }
             }
         }
 #ifdef ECCKD_TUNE
-        if constexpr (!SW && sizeof(Real) == 8) {
+        if constexpr (!SW) {
             static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+            if (v == 41) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4, 0, 18>(m, cg, a, mix, s);
+            if (v == 42) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 3, 0, 18>(m, cg, a, mix, s);
             if (v == 31) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 3>(m, cg, a, mix, s);
             if (v == 32) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 3>(m, cg, a, mix, s);
             if (v == 33) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 2, false, 1, 3>(m, cg, a, mix, s);
@@ -1106,7 +1112,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
 #endif
         // writer-warp path (fp32, odd ncol, unaligned outputs)
         if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 8, 0, 6>(m, cg, a, mix, s);
-        else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4>(m, cg, a, mix, s);
+        else return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4, 0, 18>(m, cg, a, mix, s);
     }
     return launch_walk_t<Real, SW, 8, 8, 2, 3, 4, 1, false, 1, 4>(m, cg, a, mix, s);
 }
