@@ -1044,41 +1044,31 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
 #ifdef ECCKD_TUNE
+                    // tuning build: ECCKD_WALK_VARIANT selects an alternative instantiation (tools/tune.sh)
+                    //   100 + RF      refill flavour RF at the default geometry
+                    //   LW 1..5       2 / 4 / 6 / 8 Planck warps, 3 index warps      LW 6..8   ring of 4 / 8 / 16 tiles
+                    //   SW 1..2       ring of 4 / 16 tiles
                     static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
+#define ECCKD_VARIANT(n, ...) if (v == (n)) return launch_walk_t<Real, SW, __VA_ARGS__>(m, cg, a, mix, s, &maps);
 #define ECCKD_RF_CASE(rf) \
-                    if (v == 100 + rf) { \
-                        if constexpr (SW) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, rf>(m, cg, a, mix, s, &maps); \
-                        else return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, rf>(m, cg, a, mix, s, &maps); \
-                    }
-                    ECCKD_RF_CASE(6) ECCKD_RF_CASE(7)
-                    ECCKD_RF_CASE(14) ECCKD_RF_CASE(22) ECCKD_RF_CASE(23) ECCKD_RF_CASE(18) ECCKD_RF_CASE(19)
-#undef ECCKD_RF_CASE
+                    if constexpr (SW) { ECCKD_VARIANT(100 + rf, 2, 16, 1, 8, 4, 1, true, 1, 8, 0, rf) } \
+                    else { ECCKD_VARIANT(100 + rf, 2, 16, 1, 12, 4, 1, true, 1, 3, 0, rf) }
+                    ECCKD_RF_CASE(6) ECCKD_RF_CASE(7) ECCKD_RF_CASE(14) ECCKD_RF_CASE(18) ECCKD_RF_CASE(22) ECCKD_RF_CASE(23)
                     if constexpr (SW) {
-                        if (v == 15) return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
-                        if (v == 16) return launch_walk_t<Real, SW, 2, 16, 1, 6, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
-                        if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 3, 4, 1, true, 1, 8, 0, 14>(m, cg, a, mix, s, &maps);
-                        if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 1>(m, cg, a, mix, s, &maps);
-                        if (v == 2) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 8, 2>(m, cg, a, mix, s, &maps);
+                        ECCKD_VARIANT(1, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14)
+                        ECCKD_VARIANT(2, 2, 16, 1, 16, 4, 1, true, 1, 8, 0, 14)
+                    } else {
+                        ECCKD_VARIANT(1, 2, 16, 1, 12, 4, 1, true, 1, 2, 0, 18)
+                        ECCKD_VARIANT(2, 2, 16, 1, 12, 4, 1, true, 1, 4, 0, 18)
+                        ECCKD_VARIANT(3, 2, 16, 1, 12, 4, 1, true, 1, 6, 0, 18)
+                        ECCKD_VARIANT(4, 2, 16, 1, 12, 4, 1, true, 1, 8, 0, 18)
+                        ECCKD_VARIANT(5, 2, 16, 1, 12, 3, 1, true, 1, 3, 0, 18)
+                        ECCKD_VARIANT(6, 2, 16, 1, 4, 4, 1, true, 1, 3, 0, 18)
+                        ECCKD_VARIANT(7, 2, 16, 1, 8, 4, 1, true, 1, 3, 0, 18)
+                        ECCKD_VARIANT(8, 2, 16, 1, 16, 4, 1, true, 1, 3, 0, 18)
                     }
-                    if constexpr (!SW) {
-                        if (v == 1) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
-                        if (v == 3) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 11>(m, cg, a, mix, s, &maps);
-                        if (v == 5) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 6>(m, cg, a, mix, s, &maps);
-                        if (v == 6) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 7>(m, cg, a, mix, s, &maps);
-                        if (v == 7) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 10) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 2>(m, cg, a, mix, s, &maps);
-                        if (v == 11) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 1>(m, cg, a, mix, s, &maps);
-                        if (v == 12) return launch_walk_t<Real, SW, 2, 16, 1, 12, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 15) return launch_walk_t<Real, SW, 2, 16, 1, 4, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 16) return launch_walk_t<Real, SW, 2, 16, 1, 6, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 18) return launch_walk_t<Real, SW, 2, 16, 1, 10, 4, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 19) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
-                        if (v == 13) return launch_walk_t<Real, SW, 2, 16, 1, 16, 3, 1, true, 1, 3>(m, cg, a, mix, s, &maps);
-                        if (v == 14) return launch_walk_t<Real, SW, 2, 16, 1, 16, 2, 1, true, 1, 2>(m, cg, a, mix, s, &maps);
-                        if (v == 8) return launch_walk_t<Real, SW, 2, 16, 1, 16, 4, 1, true, 1, 5>(m, cg, a, mix, s, &maps);
-                        if (v == 9) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 1, true, 1, 4>(m, cg, a, mix, s, &maps);
-                    }
+#undef ECCKD_RF_CASE
+#undef ECCKD_VARIANT
 #endif
                     // one column per compute warp (16 warps): measured faster than two columns x 8 warps
                     // refill flavour (RF) and Planck-warp count as measured on B200: SW prefers the branchy, late refill
@@ -1088,26 +1078,11 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
             }
         }
 #ifdef ECCKD_TUNE
-        if constexpr (!SW) {
+        if constexpr (!SW) {   // writer-warp path, longwave: 21..23 = 2 writer warps + 3 Planck warps with 2- / 4-layer tiles, 3 writer warps
             static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
-            if (v == 41) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 4, 0, 18>(m, cg, a, mix, s);
-            if (v == 42) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 4, false, 1, 3, 0, 18>(m, cg, a, mix, s);
-            if (v == 31) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 3>(m, cg, a, mix, s);
-            if (v == 32) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 3>(m, cg, a, mix, s);
-            if (v == 33) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 2, false, 1, 3>(m, cg, a, mix, s);
-            if (v == 34) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 1, false, 1, 3>(m, cg, a, mix, s);
-            if (v == 35) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 3, false, 1, 3>(m, cg, a, mix, s);
-            if (v == 21) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 6>(m, cg, a, mix, s);
-            if (v == 22) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 6>(m, cg, a, mix, s);
-            if (v == 23) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 1, false, 1, 7>(m, cg, a, mix, s);
-            if (v == 24) return launch_walk_t<Real, SW, 2, 16, 4, 3, 4, 1, false, 1, 7>(m, cg, a, mix, s);
-            if (v == 11) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 2, false, 1, 8>(m, cg, a, mix, s);
-            if (v == 12) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 8>(m, cg, a, mix, s);
-            if (v == 13) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 10>(m, cg, a, mix, s);
-            if (v == 14) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 3, false, 1, 9>(m, cg, a, mix, s);
-            if (v == 15) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 10>(m, cg, a, mix, s);
-            if (v == 16) return launch_walk_t<Real, SW, 2, 16, 2, 6, 4, 4, false, 1, 8>(m, cg, a, mix, s);
-            if (v == 17) return launch_walk_t<Real, SW, 2, 16, 1, 8, 4, 4, false, 1, 8>(m, cg, a, mix, s);
+            if (v == 21) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 3, 0, 18>(m, cg, a, mix, s);
+            if (v == 22) return launch_walk_t<Real, SW, 2, 16, 4, 2, 4, 2, false, 1, 3, 0, 18>(m, cg, a, mix, s);
+            if (v == 23) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 3, false, 1, 3, 0, 18>(m, cg, a, mix, s);
         }
 #endif
         // writer-warp path (fp32, odd ncol, unaligned outputs)
