@@ -327,6 +327,17 @@ def test_large_block_properties(dtype, dev, gpu_models, ck_models, c_oracles):
         assert torch.equal(o2["tau"], out["tau"][:4096][perm])
 
 
+@pytest.mark.parametrize("ncol", [18922, 18921], ids=["even-tma", "odd-writer"])
+def test_persistent_blocks_with_ragged_last_chunk(ncol, dev, gpu_models, ck_models, c_oracles):
+    """Enough columns for the persistent two-tile-chunk geometry (1183 tiles: the last chunk holds one tile, the last
+    tile 10 / 9 columns), few layers so that the oracle covers every column; even ncol takes the TMA path, odd ncol
+    the writer-warp path."""
+    inp = atm_numpy(synthetic.make_atmosphere(ncol, 3))
+    for key in ("lw_fsck", "lw_rrtmgp", "sw_wide"):
+        out = run_gpu(gpu_models[key], *inp, torch.float64, dev, ecckd_b200.KERNEL_WALK)
+        check(out, run_oracle(c_oracles[key], ck_models[key], *inp), 1e-12, f"{key}/ncol={ncol}")
+
+
 def test_linearity_in_a_linear_gas(dev, gpu_models):
     """tau is affine in the concentration of a code-1 gas: tau(2x) - tau(x) == tau(x) - tau(0) to rounding."""
     plev, tlay, tlev, tsfc, gases = _small()
