@@ -208,13 +208,13 @@ __device__ __forceinline__ double fma_(double a, double b, double c) { return __
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
-// a / b to within an ulp without the IEEE-division slow path: hardware reciprocal seed (20+ bits), two Newton steps,
-// one residual correction.  ssa = tau_rayleigh / tau only has to meet 1e-12, not correct rounding.
+// a / b to within an ulp without the IEEE-division slow path: hardware reciprocal seed (20 bits), one Newton step
+// (40 bits), and a residual correction of the quotient that squares that error again.  ssa = tau_rayleigh / tau only
+// has to meet 1e-12, not correct rounding.
 __device__ __forceinline__ double div_fast(double a, double b)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    r = __fma_rn(r, __fma_rn(-b, r, 1.0), r);
     r = __fma_rn(r, __fma_rn(-b, r, 1.0), r);
     const double q = __dmul_rn(a, r);
     return __fma_rn(__fma_rn(-b, q, a), r, q);
@@ -1047,7 +1047,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     // tuning build: ECCKD_WALK_VARIANT selects an alternative instantiation (tools/tune.sh)
                     //   100 + RF      refill flavour RF at the default geometry
                     //   LW 1..5       2 / 4 / 6 / 8 Planck warps, 3 index warps      LW 6..8   ring of 4 / 8 / 16 tiles
-                    //   SW 1..2       ring of 4 / 16 tiles
+                    //   SW 1..2       ring of 4 / 16 tiles      SW 3      3 index warps (20 warps: 96 registers per thread)
                     static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
 #define ECCKD_VARIANT(n, ...) if (v == (n)) return launch_walk_t<Real, SW, __VA_ARGS__>(m, cg, a, mix, s, &maps);
 #define ECCKD_RF_CASE(rf) \
@@ -1057,6 +1057,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     if constexpr (SW) {
                         ECCKD_VARIANT(1, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14)
                         ECCKD_VARIANT(2, 2, 16, 1, 16, 4, 1, true, 1, 8, 0, 14)
+                        ECCKD_VARIANT(3, 2, 16, 1, 8, 3, 1, true, 1, 8, 0, 14)
                     } else {
                         ECCKD_VARIANT(1, 2, 16, 1, 12, 4, 1, true, 1, 2, 0, 18)
                         ECCKD_VARIANT(2, 2, 16, 1, 12, 4, 1, true, 1, 4, 0, 18)
