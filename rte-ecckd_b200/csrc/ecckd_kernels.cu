@@ -228,6 +228,15 @@ __device__ __forceinline__ Real bil4(Real c0, Real c1, Real c2, Real c3, K k0, K
     return fma_(c3, (Real)k3, fma_(c2, (Real)k2, fma_(c1, (Real)k1, mul_(c0, (Real)k0))));
 }
 
+// sleep between barrier probes (ns) of the store warp (a ring of tiles ahead of it) and the index warps (32 layers ahead)
+#ifndef ECCKD_STORE_NAP
+#define ECCKD_STORE_NAP 100
+#endif
+#ifndef ECCKD_INDEX_NAP
+#define ECCKD_INDEX_NAP 400
+#endif
+constexpr unsigned kStoreNap = ECCKD_STORE_NAP, kIndexNap = ECCKD_INDEX_NAP;
+
 // corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
 constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
 
@@ -259,6 +268,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// The same wait for roles that run far ahead of (or behind) their partner: sleep between probes instead of spinning.
+// Every probe is an LSU instruction, and the L1 data pipe is this kernel's busiest unit (measured: the spinning store
+// and index warps added 6 probes per layer and column to ~22 useful shared/global accesses).
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsigned parity, unsigned ns)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)   // non-blocking probe (acquire.cta)
 {
     unsigned ok;
@@ -352,8 +375,16 @@ __device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
 //   4 tile-free barrier probed before the arithmetic  8 refill issued after the staging fence ("late")
 //  16 refill issued as soon as the bilinears have read the cache, ahead of the rest of the layer's arithmetic
 // ============================================================================
-template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7>
-__global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW) * 32, 1)
+// Register rebalancing (RC > 0): the roles are padded to whole warpgroups (4 warps) and trade registers with
+// setmaxnreg -- index warps keep RI, store / Planck warps drop to RH, compute warps grow to RC.  Each setmaxnreg sits
+// inside its role's branch, which never rejoins the others: ptxas budgets registers per control-flow region.
+template <int NWW, int NPW, int RC> struct PadWarps { static constexpr int value = RC ? (4 - (NWW + NPW) % 4) % 4 : 0; };
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7,
+          int RC = 0, int RI = 64, int RH = 56>
+__global__ void __launch_bounds__((TC / CPW + NI + NWW + NPW + PadWarps<NWW, NPW, RC>::value) * 32, 1)
 walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg,
             const __grid_constant__ KernelArgs<Real> a, const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps,
             const int tiles_per_chunk)
@@ -388,7 +419,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // round because the SM's issue arbiter prefers the highest warp id: the latency-bound compute warps get priority
     // over the throughput-oriented Planck warps.
     constexpr int HB = NCW + NI + NWW;              // first helper (Planck / zero-plane) warp
-    constexpr int NWARPS = HB + NPW;
+    constexpr int NWARPS = HB + NPW + PadWarps<NWW, NPW, RC>::value;   // (+ idle warps that complete the helper warpgroup)
+    static_assert(RC == 0 || ((TC / CPW) % 4 == 0 && NI % 4 == 0), "register rebalancing works on whole warpgroups");
     const int warp = NWARPS - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int ncol = a.ncol, nlay = a.nlay;
     // Persistent blocks: the columns are cut into chunks of CH tiles of TC columns (CH = 2 for large calls: the
@@ -435,6 +467,8 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const int nround = (nlay + 31) / 32;
 
     if (ECCKD_DBG(128) && warp < HB) return;   // experiment: Planck warps only
+    if (warp >= NCW + NI) {      // ---- store / writer / helper warps (every path below returns) ----
+    if constexpr (RC > 0) reg_dec<RH>();
     // =========================== TMA store warp ==================================
     if (TMA && warp >= NCW + NI && warp < HB) {
         if (lane == 0) {
@@ -444,7 +478,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (gt >= ntile_all) continue;
                 const int col0 = gt * TC;
                 for (int n = 0; n < nlay; ++n) {            // one staging tile per layer
-                    mbar_wait(&bar_full[b], par);
+                    mbar_wait_relaxed(&bar_full[b], par, kStoreNap);
                     const Real *sb = stage + (size_t)b * TILE;
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o)
@@ -478,7 +512,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             const long long col0 = (long long)gt * TC;
             const bool c_ok = col0 + c < ncol;
             const int lay0 = n * L, nl = min(L, nlay - lay0);
-            mbar_wait(&bar_full[b], par);
+            mbar_wait_relaxed(&bar_full[b], par, kStoreNap);
             const Real *sb = stage + (size_t)b * TILE + c;
             const long long off0 = ((col0 + c) + (long long)ncol * lay0) * (long long)sizeof(Real) + plane * (g0 + gsub);
             if (c_ok && !ECCKD_DBG(1)) {
@@ -514,7 +548,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== zero-plane warps (SW) ===========================
-    if (SW && NPW >= 1 && warp >= HB) {
+    if (SW && NPW >= 1 && warp >= HB && warp < HB + NPW) {
         constexpr int LPU = 32 / TC;
         const int pw = warp - HB;
         const int c = lane % TC, lsel = lane / TC;
@@ -540,7 +574,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // of lay_source, lev_source_inc and lev_source_dec directly: these three outputs (75 % of the longwave bytes)
     // never touch the staging tiles.  lev_source_inc(:,j-1) and lev_source_dec(:,j) are both B(tlev(:,j)) (:423-424):
     // the lane of level j evaluates it once and stores it twice, so a cell costs two Planck evaluations, not three.
-    if (!SW && warp >= HB) {
+    if (!SW && warp >= HB && warp < HB + NPW) {
         if (ECCKD_DBG(64)) return;
         const int pw = warp - HB;
         const int W = CH * TC;                        // strip = chunk (W divides 32)
@@ -628,8 +662,12 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         return;
     }
 
+    return;                      // idle warps of a padded helper warpgroup
+    }
+
     // =========================== index warps =====================================
     if (warp >= NCW && warp < NCW + NI) {
+        if constexpr (RC > 0) reg_dec<RI>();
         const int iw = warp - NCW;
         int tr = 0;                                        // running round over all tiles of the block
         for (int ts = 0; ts < nslot; ++ts) {
@@ -681,7 +719,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     rec.key = (ip * kNTP + it) * kGP | mask << kMaskShift;
                     rec.pad0 = rec.pad1 = 0;
                 }
-                if (u >= 1) mbar_wait(&rec_empty[rb * TC + cs], (u - 1) & 1);
+                if (u >= 1) mbar_wait_relaxed(&rec_empty[rb * TC + cs], (u - 1) & 1, kIndexNap);
                 if (j < nlay && !(ECCKD_DBG(2) && tr > 1)) recs[(rb * TC + cs) * 32 + lane] = rec;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rec_full[rb * TC + cs]);
@@ -692,6 +730,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
 
     // =========================== compute warps ===================================
+    if constexpr (RC > 0) reg_inc<RC>();
     // warp w owns columns CPW*w .. CPW*w + CPW-1 of the tile (CPW = 2: two independent dependency chains per
     // lane, and the pair of values goes to the staging tile as one conflict-free 16-byte store)
     const int g = min(g0 + lane, ngpt - 1);     // inactive lanes shadow the last g-point; never stored
@@ -988,7 +1027,7 @@ static void walk_geometry(int ntile, bool sw, int &tiles_per_chunk, int &blocks)
 }
 
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0,
-          int RF = 7>
+          int RF = 7, int RC = 0, int RI = 64, int RH = 56>
 static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, cudaStream_t s,
                                  const TmaMaps *maps = nullptr)
 {
@@ -998,7 +1037,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     const size_t smem = sizeof(Rec<Real, NB>) * 2 * TC * 32 + sizeof(Real) * NBUF * NOUT * L * 32 * TCP +
                         ((TMA && SW) ? sizeof(Real) * 32 * TCP : 0) +
                         (2 * NBUF + 4 * TC) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW, RF>;
+    auto kern = walk_kernel<Real, SW, NB, TC, L, NBUF, NI, NWW, TMA, CPW, NPW, RF, RC, RI, RH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + TC - 1) / TC;
@@ -1006,7 +1045,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     walk_geometry(ntile, SW, tpc, blocks);
     dim3 grid((unsigned)blocks, (unsigned)((m.ngpt + kGP - 1) / kGP));
     static const TmaMaps no_maps{};
-    kern<<<grid, (TC / CPW + NI + NWW + NPW) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps, tpc);
+    kern<<<grid, (TC / CPW + NI + NWW + NPW + PadWarps<NWW, NPW, RC>::value) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps, tpc);
     return cudaGetLastError();
 }
 
@@ -1058,6 +1097,10 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                         ECCKD_VARIANT(1, 2, 16, 1, 4, 4, 1, true, 1, 8, 0, 14)
                         ECCKD_VARIANT(2, 2, 16, 1, 16, 4, 1, true, 1, 8, 0, 14)
                         ECCKD_VARIANT(3, 2, 16, 1, 8, 3, 1, true, 1, 8, 0, 14)
+                        ECCKD_VARIANT(31, 2, 16, 1, 8, 4, 1, true, 2, 8, 0, 14, 168, 64, 40)
+                        ECCKD_VARIANT(32, 2, 16, 1, 8, 4, 1, true, 2, 8, 0, 6, 168, 64, 40)
+                        ECCKD_VARIANT(33, 2, 16, 1, 8, 4, 1, true, 2, 8, 0, 22, 168, 64, 40)
+                        ECCKD_VARIANT(34, 2, 16, 1, 8, 4, 1, true, 2, 8, 0, 18, 168, 64, 40)
                     } else {
                         ECCKD_VARIANT(1, 2, 16, 1, 12, 4, 1, true, 1, 2, 0, 18)
                         ECCKD_VARIANT(2, 2, 16, 1, 12, 4, 1, true, 1, 4, 0, 18)
@@ -1067,6 +1110,10 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                         ECCKD_VARIANT(6, 2, 16, 1, 4, 4, 1, true, 1, 3, 0, 18)
                         ECCKD_VARIANT(7, 2, 16, 1, 8, 4, 1, true, 1, 3, 0, 18)
                         ECCKD_VARIANT(8, 2, 16, 1, 16, 4, 1, true, 1, 3, 0, 18)
+                        ECCKD_VARIANT(31, 2, 16, 1, 12, 4, 1, true, 2, 3, 0, 18, 168, 64, 56)
+                        ECCKD_VARIANT(32, 2, 16, 1, 12, 4, 1, true, 2, 3, 0, 6, 168, 64, 56)
+                        ECCKD_VARIANT(33, 2, 16, 1, 12, 4, 1, true, 2, 3, 0, 22, 168, 64, 56)
+                        ECCKD_VARIANT(34, 2, 16, 1, 12, 4, 1, true, 2, 3, 0, 14, 168, 64, 56)
                     }
 #undef ECCKD_RF_CASE
 #undef ECCKD_VARIANT
