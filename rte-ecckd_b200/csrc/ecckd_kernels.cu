@@ -352,22 +352,28 @@ __device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
 }
 
 // ============================================================================
-// walk_kernel: a three-role, warp-specialised pipeline inside one block
+// walk_kernel: a warp-specialised pipeline inside one persistent block
 //
-//   index warps   (NI)  lane l computes the interpolation record of layer j0+l of
-//                       one column: log-pressure / temperature / mole-fraction /
-//                       Planck indices and weights -- long dependent chains (log,
-//                       IEEE divisions), one chunk of 32 layers ahead of the walk
-//   compute warps (TC)  one column each, lanes = g-points: walk the layers top to
-//                       bottom, corner rows cached in registers, accumulate tau and
-//                       the sources, write them transposed into a ring of staging
-//                       tiles [output][layer][g][column]
-//   writer warps  (NWW) turn finished tiles into full-line, column-contiguous
-//                       streaming stores
+//   index warps   (NI)   lane l computes the interpolation record of layer j0+l of
+//                        one column: log-pressure / temperature / mole-fraction
+//                        indices and weights -- long dependent chains (log, IEEE
+//                        divisions), one chunk of 32 layers ahead of the walk
+//   compute warps (TC/CPW) one column each, lanes = g-points: walk the layers top to
+//                        bottom, corner rows cached in registers, accumulate tau (and
+//                        ssa), write them transposed into a ring of staging tiles
+//                        [output][layer][g][column]
+//   store warp    (TMA)  one thread turns finished tiles into cp.async.bulk.tensor
+//                        stores of the caller's (ncol, nlay, ngpt) arrays; or
+//   writer warps  (NWW)  the same with full-line streaming stores (fp32, odd ncol)
+//   Planck warps  (NPW)  longwave: lanes = (column, level), interpolate the Planck
+//                        LUT from shared memory and store lay_source / lev_source_inc /
+//                        lev_source_dec / sfc_source directly, bypassing the tiles
 //
 // Hand-offs are mbarrier full/empty pairs, so no role ever waits for a peer of
 // the same role: index -> compute through double-buffered per-column record
-// chunks, compute -> writer through NBUF tiles of L layers.
+// chunks, compute -> store through NBUF tiles of L layers.  A block walks chunks of
+// one or two 16-column tiles, strided by the grid (see the comment at the top of the
+// kernel body); DESIGN.md 4.2 has the measured rationale of every choice below.
 // NB = register-cached bilinear slots: slot 0 is the per-call mixed table, slots
 // 1..NB-1 the gases whose concentration varies over the call.
 // RF = flavour of the compute warps' cache refill, a bit set tuned per band on B200:
