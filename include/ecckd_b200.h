@@ -221,6 +221,11 @@ int ecckd_interpolation_indices_f64(ecckd_model *model, int dev_index, int ncol,
 int ecckd_planck_indices_f64(ecckd_model *model, int dev_index, int64_t n, const double *temperature,
                              int32_t *it0, double *w1, void *stream, char err[ECCKD_ERRLEN]);
 
+/* debug: launch geometry of the column-walking kernel for a call of `ncol` columns on a device with `sm_count` SMs --
+ * 16-column tiles are grouped into chunks of `tiles_per_chunk` (1 or 2) and block b of `blocks` walks chunks
+ * b, b + blocks, ...  Host arithmetic only (no device needed); the CPU tests check that every tile is walked once. */
+void ecckd_debug_walk_plan(int ncol, int shortwave, int sm_count, int *tiles_per_chunk, int *blocks);
+
 /* Library identification / build info ("sm_100a", table precision, ...). */
 const char *ecckd_version(void);
 

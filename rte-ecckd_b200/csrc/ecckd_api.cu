@@ -375,6 +375,15 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
 // ============================================================================
 extern "C" {
 
+void ecckd_debug_walk_plan(int ncol, int shortwave, int sm_count, int *tiles_per_chunk, int *blocks)
+{
+    int tpc = 1, nb = 1;
+    const int ntile = ncol > 0 ? (ncol + ecckd::kWalkTileCols - 1) / ecckd::kWalkTileCols : 0;
+    ecckd::walk_plan(ntile, shortwave != 0, sm_count, tpc, nb);
+    if (tiles_per_chunk) *tiles_per_chunk = tpc;
+    if (blocks) *blocks = nb;
+}
+
 const char *ecckd_version(void) { return "ecckd_b200 0.1 (sm_100a; fp32 tables promoted in-kernel, fp64 copy for the f64 path)"; }
 
 int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices, ecckd_model **out, char err[ECCKD_ERRLEN])

@@ -1007,7 +1007,23 @@ static bool encode_output_map(CUtensorMap *map, double *ptr, int ncol, int nlay,
 }
 
 // Launch geometry of the persistent walk kernel: tiles per chunk and blocks per g-group.  One block is resident
-// per SM (shared memory); a longwave call with at least four tiles per SM uses two-tile chunks.
+// per SM (shared memory).  Two-tile chunks pay in the longwave only (wider Planck stores, measured 8 %), and only
+// when the coarser granularity does not unbalance the blocks: compare the longest block under both choices.
+// Pure host arithmetic (exported for the CPU tests as ecckd_debug_walk_plan).
+void walk_plan(int ntile, bool sw, int sms, int &tiles_per_chunk, int &blocks)
+{
+    if (sms < 1) sms = 1;
+    tiles_per_chunk = 1;
+    if (!sw && ntile >= 4 * sms) {
+        const int n2 = (ntile + 1) / 2;
+        const double t1 = 1.08 * ((ntile + sms - 1) / sms), t2 = 2.0 * ((n2 + sms - 1) / sms);
+        if (t2 <= t1) tiles_per_chunk = 2;
+    }
+    const int nchunk = (ntile + tiles_per_chunk - 1) / tiles_per_chunk;
+    blocks = nchunk < sms ? nchunk : sms;
+    if (blocks < 1) blocks = 1;
+}
+
 static void walk_geometry(int ntile, bool sw, int &tiles_per_chunk, int &blocks)
 {
     static const int sms = [] {
@@ -1015,21 +1031,15 @@ static void walk_geometry(int ntile, bool sw, int &tiles_per_chunk, int &blocks)
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
         return n;
     }();
-    // Two-tile chunks pay in the longwave only (wider Planck stores, measured 8 %), and only when the coarser
-    // granularity does not unbalance the blocks: compare the longest block under both choices.
-    tiles_per_chunk = 1;
-    if (!sw && ntile >= 4 * sms) {
-        const int n2 = (ntile + 1) / 2;
-        const double t1 = 1.08 * ((ntile + sms - 1) / sms), t2 = 2.0 * ((n2 + sms - 1) / sms);
-        if (t2 <= t1) tiles_per_chunk = 2;
-    }
-    int cap = sms;
+    walk_plan(ntile, sw, sms, tiles_per_chunk, blocks);
 #ifdef ECCKD_TUNE
-    if (getenv("ECCKD_CH")) tiles_per_chunk = atoi(getenv("ECCKD_CH"));
-    if (getenv("ECCKD_BLOCKS")) cap = atoi(getenv("ECCKD_BLOCKS"));
+    if (getenv("ECCKD_CH") || getenv("ECCKD_BLOCKS")) {
+        if (getenv("ECCKD_CH")) tiles_per_chunk = atoi(getenv("ECCKD_CH"));
+        const int cap = getenv("ECCKD_BLOCKS") ? atoi(getenv("ECCKD_BLOCKS")) : sms;
+        const int nchunk = (ntile + tiles_per_chunk - 1) / tiles_per_chunk;
+        blocks = nchunk < cap ? nchunk : cap;
+    }
 #endif
-    const int nchunk = (ntile + tiles_per_chunk - 1) / tiles_per_chunk;
-    blocks = nchunk < cap ? nchunk : cap;
 }
 
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA = false, int CPW = 1, int NPW_LW = 8, int NPW_SW = 0,

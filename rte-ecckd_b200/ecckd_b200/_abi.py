@@ -45,6 +45,7 @@ _names = C.POINTER(C.c_char_p)
 _views = C.POINTER(VmrView)
 _SIGS = {
     "ecckd_version": (C.c_char_p, []),
+    "ecckd_debug_walk_plan": (None, [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ecckd_model_create": (_i, [C.POINTER(HostTables), _i, C.POINTER(C.c_int), C.POINTER(_vp), _cp]),
     "ecckd_model_load": (_i, [_cp, _i, C.POINTER(C.c_int), C.POINTER(_vp), _cp]),
     "ecckd_model_destroy": (None, [_vp]),

@@ -135,3 +135,42 @@ def test_world_size_2_gloo_column_sharding(ck_models, c_oracles):
     from conftest import rel_err
     assert rel_err(cols, out["tau"][:, 3, 5]) <= 1e-12    # sharded == unsharded (inputs equal to rounding, see above)
     assert [g[:2] for g in sorted(gathered)] == [(0, 11), (11, 21)]
+
+
+def _walk_plan(ncol, shortwave, sms):
+    import ctypes as C
+    lib = ecckd_b200.load_library()
+    tpc, blocks = C.c_int(0), C.c_int(0)
+    lib.ecckd_debug_walk_plan(ncol, int(shortwave), sms, C.byref(tpc), C.byref(blocks))
+    return tpc.value, blocks.value
+
+
+@pytest.mark.parametrize("sms", [1, 4, 148])
+@pytest.mark.parametrize("shortwave", [False, True])
+def test_walk_plan_covers_every_tile_exactly_once(shortwave, sms):
+    """The persistent walk kernel's launch geometry (host arithmetic, no device): block b of `blocks` walks chunks
+    b, b + blocks, ... of `tiles_per_chunk` 16-column tiles.  Replay the kernel's tile_of() enumeration and check the
+    partition; also the policy: two-tile chunks only in the longwave, only for large calls, never unbalancing."""
+    for ncol in [1, 15, 16, 17, 70, 1800, 2368, 9472, 9473, 16384, 18921, 18922, 32768, 65536, 65535, 100000, 1048576]:
+        tpc, blocks = _walk_plan(ncol, shortwave, sms)
+        ntile = (ncol + 15) // 16
+        nchunk_all = (ntile + tpc - 1) // tpc
+        assert tpc in (1, 2) and 1 <= blocks <= max(1, min(sms, nchunk_all))
+        if shortwave or ntile < 4 * sms:
+            assert tpc == 1
+        seen = np.zeros(ntile, dtype=np.int32)
+        longest = 0
+        for b in range(blocks):
+            nchunk = (nchunk_all - b + blocks - 1) // blocks          # as in walk_kernel
+            assert nchunk >= 1
+            mine = 0
+            for ts in range(nchunk * tpc):
+                k = ts // tpc
+                gt = (b + k * blocks) * tpc + (ts - k * tpc)
+                if gt < ntile:
+                    seen[gt] += 1
+                    mine += 1
+            longest = max(longest, mine)
+        assert (seen == 1).all(), f"ncol={ncol}: tiles walked {seen.min()}..{seen.max()} times"
+        # balance: the longest block is within one chunk of the ideal share
+        assert longest <= -(-ntile // blocks) + tpc - 1 + (tpc - 1)
