@@ -338,6 +338,20 @@ def test_persistent_blocks_with_ragged_last_chunk(ncol, dev, gpu_models, ck_mode
         check(out, run_oracle(c_oracles[key], ck_models[key], *inp), 1e-12, f"{key}/ncol={ncol}")
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_persistent_blocks_with_several_varying_gases(dtype, dev, gpu_models, ck_models, c_oracles):
+    """More than one bilinear gas varying over the call selects the 8-slot instantiation (8-column tiles, writer
+    warps); 9470 columns put it into the persistent two-tile-chunk geometry (1184 tiles, the last one ragged)."""
+    ncol, nlay = 9470, 3
+    plev, tlay, tlev, tsfc, gases = atm_numpy(synthetic.make_atmosphere(ncol, nlay))
+    wobble = 1 + 0.2 * np.cos(np.arange(tlay.size)).reshape(tlay.shape, order="F")
+    gl = [(n, v if isinstance(v, np.ndarray) else (np.asfortranarray(v * wobble) if n in ("co2", "ch4", "n2o") else v))
+          for n, v in gases]
+    for key in ("lw_fsck", "sw_wide"):
+        out = run_gpu(gpu_models[key], plev, tlay, tlev, tsfc, gl, dtype, dev, ecckd_b200.KERNEL_WALK)
+        check(out, run_oracle(c_oracles[key], ck_models[key], plev, tlay, tlev, tsfc, gl, dtype), TOL[dtype], f"{key}/nvar=4")
+
+
 def test_linearity_in_a_linear_gas(dev, gpu_models):
     """tau is affine in the concentration of a code-1 gas: tau(2x) - tau(x) == tau(x) - tau(0) to rounding."""
     plev, tlay, tlev, tsfc, gases = _small()
