@@ -53,11 +53,14 @@ extern "C" {
 #define ECCKD_ERR_REFERENCE 3
 #define ECCKD_ERR_IO 4
 
-/* Kernel selection for the compute entry points (tests exercise both; AUTO picks
- * the column-walking kernel whenever the call qualifies). */
+/* Kernel selection for the compute entry points (the tests exercise every one; AUTO
+ * picks the fastest kernel the call qualifies for: QUAD, else COLWALK, else GENERIC). */
 #define ECCKD_KERNEL_AUTO 0
-#define ECCKD_KERNEL_WALK 1    /* warp-per-column layer walk, smem-staged coalesced stores */
+#define ECCKD_KERNEL_WALK 1    /* a table-walking kernel (QUAD when the call qualifies, else COLWALK); error if neither */
 #define ECCKD_KERNEL_GENERIC 2 /* thread-per-(column,layer); any table shape / gas mix */
+#define ECCKD_KERNEL_QUAD 3    /* the product path: 4 columns per warp, TMA tensor stores (needs 16-byte aligned outputs
+                                  and a column count that is a multiple of 16 bytes: even for fp64, of 4 for fp32) */
+#define ECCKD_KERNEL_COLWALK 4 /* one column per warp; writer-warp stores for odd column counts / unaligned outputs */
 
 typedef struct ecckd_model ecckd_model; /* opaque: device-resident packed tables */
 

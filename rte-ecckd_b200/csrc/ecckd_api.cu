@@ -194,13 +194,22 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
         a.out[0] = o0;
         if (sw) { a.out[1] = not_2str ? nullptr : o1; a.out[2] = not_2str ? nullptr : o2; a.out[3] = nullptr; a.out2d = not_2str ? nullptr : o2d; }
         else { a.out[1] = o1; a.out[2] = lev_missing ? nullptr : o2; a.out[3] = lev_missing ? nullptr : o3; a.out2d = o2d; }
-        // the walking kernel indexes outputs with 32-bit element offsets
-        if ((long long)ncol * nlay * M->ngpt >= (1ll << 31)) walk_ok = false;
+        // the one-column-per-warp walk kernel indexes outputs with 32-bit element offsets; the quad kernel has no such limit
+        const bool big = (long long)ncol * nlay * M->ngpt >= (1ll << 31);
+        const bool quad_ok = walk_ok && quad_eligible<Real>(cg, a);
+        const bool colwalk_ok = walk_ok && !big;
         bool use_walk;
-        if (kernel == ECCKD_KERNEL_AUTO) use_walk = walk_ok;
+        int which = 0;
+        if (kernel == ECCKD_KERNEL_AUTO) { use_walk = quad_ok || colwalk_ok; which = quad_ok ? 1 : 2; }
         else if (kernel == ECCKD_KERNEL_WALK) {
-            if (!walk_ok) { set_err(err, "ecckd: call does not qualify for the walking kernel"); return ECCKD_ERR_ARG; }
-            use_walk = true;
+            if (!quad_ok && !colwalk_ok) { set_err(err, "ecckd: call does not qualify for the walking kernel"); return ECCKD_ERR_ARG; }
+            use_walk = true; which = quad_ok ? 1 : 2;
+        } else if (kernel == ECCKD_KERNEL_QUAD) {
+            if (!quad_ok) { set_err(err, "ecckd: call does not qualify for the quad kernel"); return ECCKD_ERR_ARG; }
+            use_walk = true; which = 1;
+        } else if (kernel == ECCKD_KERNEL_COLWALK) {
+            if (!colwalk_ok) { set_err(err, "ecckd: call does not qualify for the walking kernel"); return ECCKD_ERR_ARG; }
+            use_walk = true; which = 2;
         } else if (kernel == ECCKD_KERNEL_GENERIC) use_walk = false;
         else { set_err(err, "ecckd: unknown kernel selector"); return ECCKD_ERR_ARG; }
         cudaError_t e;
@@ -208,7 +217,7 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
             // stream-ordered scratch for the per-call mixed table: safe for concurrent calls on other streams
             void *scratch = nullptr;
             CUDA_TRY(cudaMallocAsync(&scratch, walk_scratch_bytes(d.dm, cg, sizeof(Real)), stream));
-            e = sw ? launch_walk<Real, true>(d.dm, cg, a, scratch, stream) : launch_walk<Real, false>(d.dm, cg, a, scratch, stream);
+            e = sw ? launch_walk<Real, true>(d.dm, cg, a, scratch, stream, which) : launch_walk<Real, false>(d.dm, cg, a, scratch, stream, which);
             cudaError_t e2 = cudaFreeAsync(scratch, stream);
             CUDA_TRY(e);
             CUDA_TRY(e2);
@@ -495,7 +504,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
                     if (g >= ng) continue;
                     for (int ip = 0; ip < np; ++ip)
                         for (int it = 0; it < nt; ++it) {
-                            const size_t cell = ((size_t)ip * kNTP + it) * kGP + ln;
+                            const size_t cell = ((size_t)ip * kNTP + it) * kGP + walk_pos(ln);
                             const size_t src = (size_t)g + (size_t)ng * (ip + (size_t)np * it);
                             for (int q = 0; q < nslot; ++q)
                                 wbil64[((size_t)grp * nslot + q) * kSlab + cell] = k64[slot_off[q] + src];
@@ -534,6 +543,8 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         ds->device = dev;
         DevModel &dm = ds->dm;
         dm.ngpt = t->ngpt; dm.np = t->npress; dm.nt = t->ntemp; dm.nplanck = M->nplanck;
+        dm.sm_count = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&dm.sm_count, cudaDevAttrMultiProcessorCount, dev));
         dm.logp0 = t->log_pressure[0];
         dm.dlogp = t->log_pressure[1] - t->log_pressure[0];
         dm.dt = t->temperature[t->npress] - t->temperature[0];                           // temperature(1,2)-temperature(1,1)

@@ -22,12 +22,17 @@ constexpr int kGP = 32;                    // g-points per group = lanes per war
 constexpr int kNTP = 8;                    // padded temperature extent   (ntemp  <= 8)
 constexpr int kNPP = 64;                   // padded pressure extent      (npress <= 64)
 constexpr int kSlab = kNPP * kNTP * kGP;   // elements of one (slot | mole-fraction) slab
+// Position of g-point l (0..31) of a group inside a 32-element table row.  Rows are stored permuted so that the four
+// g-points {q, q+8, q+16, q+24} of one thread of the quad kernel (8 lanes per column, 4 g-points per lane) are one
+// 16/32-byte vector, while their rows in the 128-byte-swizzled staging tile (swizzle key = g & 7 = q) stay conflict-free.
+__host__ __device__ constexpr int walk_pos(int l) { return ((l & 7) << 2) | (l >> 3); }
 
 enum Code : int { kNone = 0, kLinear = 1, kLut = 2, kRelLinear = 3 };  // :54-57
 
 // Device-resident packed tables (one copy per GPU, read-only after create).
 struct DevModel {
     int ngpt, np, nt, nplanck;
+    int sm_count;      // multiprocessors of the device this copy lives on (persistent-grid size)
     double logp0;      // log_pressure(1)                              :104
     double dlogp;      // log_pressure(2) - log_pressure(1)            :105
     double dt;         // temperature(1,2) - temperature(1,1)          :106

@@ -21,10 +21,9 @@
 //                     cross-check of walk_kernel in the GPU tests.
 #include "ecckd_device.cuh"
 #include "ecckd_kernels.h"
+#include "ecckd_pipeline.cuh"
 #include <cstdlib>
 #include <cstdint>
-#include <cuda.h>
-#include <cudaTypedefs.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace ecckd {
 
@@ -175,182 +174,6 @@ template <typename Real, int NB> struct alignas(16) Rec {
 };
 constexpr int kMaskShift = 16, kMaskLut = 0x100 << kMaskShift, kMaskNeg = 0x200 << kMaskShift;
 
-template <typename Real> __device__ __forceinline__ void lds4(const Real *p, Real &a, Real &b, Real &c, Real &d);
-template <> __device__ __forceinline__ void lds4<double>(const double *p, double &a, double &b, double &c, double &d)
-{
-    const double2 u = *reinterpret_cast<const double2 *>(p), v = *reinterpret_cast<const double2 *>(p + 2);
-    a = u.x; b = u.y; c = v.x; d = v.y;
-}
-template <> __device__ __forceinline__ void lds4<float>(const float *p, float &a, float &b, float &c, float &d)
-{
-    const float4 u = *reinterpret_cast<const float4 *>(p);
-    a = u.x; b = u.y; c = u.z; d = u.w;
-}
-template <typename Real> __device__ __forceinline__ void lds2(const Real *p, Real &a, Real &b);
-template <> __device__ __forceinline__ void lds2<double>(const double *p, double &a, double &b)
-{
-    const double2 u = *reinterpret_cast<const double2 *>(p);
-    a = u.x; b = u.y;
-}
-template <> __device__ __forceinline__ void lds2<float>(const float *p, float &a, float &b)
-{
-    const float2 u = *reinterpret_cast<const float2 *>(p);
-    a = u.x; b = u.y;
-}
-
-// Explicit rounding / fusion: every instantiation of the walking kernel (TMA or writer-warp path, any tile
-// shape) must produce bit-identical values, so that column shards, host blocks and odd/even ncol agree bitwise.
-__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
-__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
-// a / b to within an ulp without the IEEE-division slow path: hardware reciprocal seed (20 bits), one Newton step
-// (40 bits), and a residual correction of the quotient that squares that error again.  ssa = tau_rayleigh / tau only
-// has to meet 1e-12, not correct rounding.
-__device__ __forceinline__ double div_fast(double a, double b)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    r = __fma_rn(r, __fma_rn(-b, r, 1.0), r);
-    const double q = __dmul_rn(a, r);
-    return __fma_rn(__fma_rn(-b, q, a), r, q);
-}
-__device__ __forceinline__ float div_fast(float a, float b) { return __fdiv_rn(a, b); }
-
-// c0*k0 + c1*k1 + c2*k2 + c3*k3 as one fused chain
-template <typename Real, typename K>
-__device__ __forceinline__ Real bil4(Real c0, Real c1, Real c2, Real c3, K k0, K k1, K k2, K k3)
-{
-    return fma_(c3, (Real)k3, fma_(c2, (Real)k2, fma_(c1, (Real)k1, mul_(c0, (Real)k0))));
-}
-
-// sleep between barrier probes (ns) of the store warp (a ring of tiles ahead of it) and the index warps (32 layers ahead)
-#ifndef ECCKD_STORE_NAP
-#define ECCKD_STORE_NAP 100
-#endif
-#ifndef ECCKD_INDEX_NAP
-#define ECCKD_INDEX_NAP 400
-#endif
-constexpr unsigned kStoreNap = ECCKD_STORE_NAP, kIndexNap = ECCKD_INDEX_NAP;
-
-// corner offsets inside a slab (elements): (ip,it) (ip+1,it) (ip,it+1) (ip+1,it+1)
-constexpr int kC00 = 0, kC10 = kNTP * kGP, kC01 = kGP, kC11 = kNTP * kGP + kGP;
-
-// experiment switches of the tuning build (ECCKD_DBG environment variable); compiled out of the production library
-#ifdef ECCKD_TUNE
-#define ECCKD_DBG(bit) ((a.dbg & (bit)) != 0)
-#else
-#define ECCKD_DBG(bit) false
-#endif
-
-// ---- mbarrier helpers (shared::cta, generic proxy only) -------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)   // release.cta
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)   // acquire.cta
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// The same wait for roles that run far ahead of (or behind) their partner: sleep between probes instead of spinning.
-// Every probe is an LSU instruction, and the L1 data pipe is this kernel's busiest unit (measured: the spinning store
-// and index warps added 6 probes per layer and column to ~22 useful shared/global accesses).
-__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsigned parity, unsigned ns)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "nanosleep.u32 %2;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)   // non-blocking probe (acquire.cta)
-{
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Make a loop-invariant value opaque to the optimiser, so that it is kept in a register instead of being
-// rematerialised from kernel parameters and special registers in every iteration of the layer loop.
-template <typename T> __device__ __forceinline__ void keep(const T *&p) { asm volatile("" : "+l"(p)); }
-__device__ __forceinline__ void keep(int &v) { asm volatile("" : "+r"(v)); }
-__device__ __forceinline__ void keep(unsigned &v) { asm volatile("" : "+r"(v)); }
-// the same barrier operations on a precomputed shared-window address (saves the generic -> shared conversion per use)
-__device__ __forceinline__ void mbar_arrive_a(unsigned addr)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool mbar_test_a(unsigned addr, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-// ---- TMA (cp.async.bulk.tensor) store helpers ------------------------------------
-struct TmaMaps { alignas(64) CUtensorMap m[4]; };
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Predicated global load that writes its destination register directly (tied operand): the refill of
-// the register cache stays branch-free and, more importantly, nothing has to wait for the data until
-// the value is really used one layer later (a compiler-generated load + MOV would stall on the MOV).
-__device__ __forceinline__ void ldg_if(double &dst, const double *p, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(dst) : "l"(p), "r"((int)pred));
-}
-__device__ __forceinline__ void ldg_if(float &dst, const float *p, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}" : "+f"(dst) : "l"(p), "r"((int)pred));
-}
-
-// predicated streaming store (keeps the Planck g-loop free of divergent branches)
-__device__ __forceinline__ void stcs_if(double *p, double v, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)pred) : "memory");
-}
-
 // ============================================================================
 // walk_kernel: a warp-specialised pipeline inside one persistent block
 //
@@ -385,8 +208,6 @@ __device__ __forceinline__ void stcs_if(float *p, float v, bool pred)
 // setmaxnreg -- index warps keep RI, store / Planck warps drop to RH, compute warps grow to RC.  Each setmaxnreg sits
 // inside its role's branch, which never rejoins the others: ptxas budgets registers per control-flow region.
 template <int NWW, int NPW, int RC> struct PadWarps { static constexpr int value = RC ? (4 - (NWW + NPW) % 4) % 4 : 0; };
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <typename Real, bool SW, int NB, int TC, int L, int NBUF, int NI, int NWW, bool TMA, int CPW, int NPW, int RF = 7,
           int RC = 0, int RI = 64, int RH = 56>
@@ -745,9 +566,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // LUT gas (eight values per layer) is cached at full width, because the conversion pipe (16 lanes/clk/SM) is
     // shared with the Planck warps and eight more F2F per layer measurably slow both; the per-call mixed table, a
     // sum of products, needs the full Real width anyway.
-    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + lane;
-    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + lane;
-    const Real *wmix = mixtab + (size_t)grp * kSlab + lane;          // negative-sign copy at + ngroups*kSlab
+    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + walk_pos(lane);
+    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + walk_pos(lane);
+    const Real *wmix = mixtab + (size_t)grp * kSlab + walk_pos(lane);          // negative-sign copy at + ngroups*kSlab
     const float *wvar = wbil + (NB == 2 ? cg.var_off[0] : 0);       // NB == 2: the one varying gas
     if constexpr ((RF & 2) != 0) { keep(wvar); keep(wlut); keep(wmix); }
 
@@ -983,7 +804,7 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
 // launchers
 // ============================================================================
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
 {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
         void *p = nullptr;
@@ -1024,13 +845,8 @@ void walk_plan(int ntile, bool sw, int sms, int &tiles_per_chunk, int &blocks)
     if (blocks < 1) blocks = 1;
 }
 
-static void walk_geometry(int ntile, bool sw, int &tiles_per_chunk, int &blocks)
+static void walk_geometry(int ntile, bool sw, int sms, int &tiles_per_chunk, int &blocks)
 {
-    static const int sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        return n;
-    }();
     walk_plan(ntile, sw, sms, tiles_per_chunk, blocks);
 #ifdef ECCKD_TUNE
     if (getenv("ECCKD_CH") || getenv("ECCKD_BLOCKS")) {
@@ -1058,7 +874,7 @@ static cudaError_t launch_walk_t(const DevModel &m, const CallGases &cg, const K
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + TC - 1) / TC;
     int tpc, blocks;
-    walk_geometry(ntile, SW, tpc, blocks);
+    walk_geometry(ntile, SW, m.sm_count, tpc, blocks);
     dim3 grid((unsigned)blocks, (unsigned)((m.ngpt + kGP - 1) / kGP));
     static const TmaMaps no_maps{};
     kern<<<grid, (TC / CPW + NI + NWW + NPW + PadWarps<NWW, NPW, RC>::value) * 32, smem, s>>>(m, cg, a, mix, maps ? *maps : no_maps, tpc);
@@ -1079,14 +895,19 @@ size_t walk_scratch_bytes(const DevModel &m, const CallGases &, size_t real_size
 }
 
 template <typename Real, bool SW>
-cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, void *scratch, cudaStream_t s)
+cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, void *scratch, cudaStream_t s, int which)
 {
+    if (which == 1 && !quad_eligible<Real>(cg, a)) return cudaErrorInvalidValue;
     Real *mix = static_cast<Real *>(scratch);
     if (cg.nmix > 0) {
         const int n = ((m.ngpt + kGP - 1) / kGP) * kSlab;
         mix_kernel<Real><<<(n + 255) / 256, 256, 0, s>>>(m, cg, mix);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+    }
+    {   // the product path: four columns per compute warp, TMA tensor stores (ecckd_quad.cu)
+        static const bool no_quad = getenv("ECCKD_NO_QUAD") != nullptr;
+        if (which == 1 || (which == 0 && !no_quad && quad_eligible<Real>(cg, a))) return launch_quad<Real, SW>(m, cg, a, mix, m.sm_count, s);
     }
     if (cg.nvar <= 1) {
         if constexpr (sizeof(Real) == 8) {
@@ -1183,8 +1004,8 @@ cudaError_t launch_planck_indices(const DevModel &m, long long n, const double *
 }
 
 #define ECCKD_INST(Real)                                                                                               \
-    template cudaError_t launch_walk<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t); \
-    template cudaError_t launch_walk<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t);  \
+    template cudaError_t launch_walk<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t, int); \
+    template cudaError_t launch_walk<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *, cudaStream_t, int);  \
     template cudaError_t launch_generic<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t); \
     template cudaError_t launch_generic<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);  \
     template cudaError_t launch_indices<Real>(const DevModel &, const GasRef *, int, int, const Real *, const Real *, int *,   \

@@ -23,8 +23,10 @@ template <typename Real> struct KernelArgs {
 // Bytes of stream-ordered scratch launch_walk needs for the per-call mixed table (0: none).
 size_t walk_scratch_bytes(const DevModel &, const CallGases &, size_t real_size);
 // Launches the table-mixing kernel (when the call has constant-factor gases) and the walking kernel.
+// `which`: 0 = quad kernel when the call is eligible, else the one-column-per-warp walk kernel; 1 = quad kernel only
+// (cudaErrorInvalidValue when not eligible); 2 = one-column-per-warp walk kernel only.
 template <typename Real, bool SW>
-cudaError_t launch_walk(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *scratch, cudaStream_t);
+cudaError_t launch_walk(const DevModel &, const CallGases &, const KernelArgs<Real> &, void *scratch, cudaStream_t, int which = 0);
 template <typename Real, bool SW>
 cudaError_t launch_generic(const DevModel &, const CallGases &, const KernelArgs<Real> &, cudaStream_t);
 template <typename Real>
@@ -34,6 +36,12 @@ cudaError_t launch_planck_indices(const DevModel &, long long n, const double *T
 // Geometry of a walk-kernel launch over `ntile` 16-column tiles on a device with `sms` SMs: tiles per chunk (1 or 2)
 // and blocks per g-group; block b walks chunks b, b + blocks, ...  Pure host arithmetic.
 void walk_plan(int ntile, bool shortwave, int sms, int &tiles_per_chunk, int &blocks);
+// quad kernel (ecckd_quad.cu): the product path for calls whose outputs admit TMA tensor maps
+constexpr int kQuadTileCols = 32;   // columns per tile
+constexpr int kQuadMaxVar = 3;      // bilinear gases with a varying concentration it keeps in registers
+template <typename Real> bool quad_eligible(const CallGases &, const KernelArgs<Real> &);
+template <typename Real, bool SW>
+cudaError_t launch_quad(const DevModel &, const CallGases &, const KernelArgs<Real> &, const Real *mix, int sms, cudaStream_t);
 constexpr int kWalkTileCols = 16;   // columns per tile of the fp64 / fp32 walk kernels with at most one varying gas
 
 }  // namespace ecckd

@@ -1,0 +1,592 @@
+// ecckd_quad.cu -- quad_kernel, the product kernel of the ECCKD gas-optics hot path on sm_100a.
+//
+// One fused pass replaces the loop nests of /root/reference/src/gas_optics_ecckd.f90:
+//   calculate_optical_depth :117-240 (once per gas) + accumulate :370
+//   calculate_planck_function :273-288 (x3) + shifted copies :423-424
+//   calculate_rayleigh_optical_depth :313-317 + ssa/g :456-460 + toa_src :468-472
+//
+// A persistent block (one per SM) walks tiles of 32 columns top to bottom as ONE continuous stream of
+// (tile, layer) positions; four warp roles hand off through mbarriers:
+//
+//   index warps  (4)  lanes = columns.  Stream position s (a layer of a tile) belongs to warp s mod 4: coalesced loads
+//                     of plev / tlay / vmr, the reference's index arithmetic (:120-163) with IEEE divisions in its
+//                     operation order, and the interpolation record of each column written as structure-of-arrays
+//                     into a ring of R layer slots.
+//   compute warps (8) FOUR columns per warp: 8 lanes per column, 4 g-points per lane (g = q, q+8, q+16, q+24).
+//                     The record of a layer is read with 5 shared-memory loads that serve four columns at once (one
+//                     wavefront each), 16 independent bilinear chains per lane give the fp64 pipe instruction-level
+//                     parallelism, and the corner rows of the three table slots (look-up-table gas, per-call mixed
+//                     table, one varying gas) live in registers, refilled by predicated 16-byte loads when the
+//                     column's (ip0,it0[,iv0]) key moves.  tau (and ssa) go to a 128-byte-swizzled staging tile.
+//   store warp   (1)  one thread turns finished staging tiles into cp.async.bulk.tensor stores of the caller's
+//                     (ncol, nlay, ngpt) arrays (SW: the g = 0 plane comes from a zeroed tile).
+//   Planck warps (3)  longwave: lanes = columns, one level of a tile per unit; interpolate the Planck LUT from
+//                     shared memory and store lay_source / lev_source_inc / lev_source_dec / sfc_source directly
+//                     (256-byte runs).  lev_source_inc(:,j-1) and lev_source_dec(:,j) are one evaluation.
+//
+// Against round 1's one-column-per-warp kernel this runs 32 instead of 16 columns per SM in flight at a third of the
+// instructions per cell, and a quarter of the record / barrier traffic in the L1 data pipe.
+// Registers are traded between the roles with setmaxnreg (compute warps grow, the others shrink).
+// The arithmetic per g-point is the same sequence of explicitly rounded operations as in walk_kernel, so both
+// kernels produce bit-identical results.
+#include "ecckd_device.cuh"
+#include "ecckd_kernels.h"
+#include "ecckd_pipeline.cuh"
+#include <cstdlib>
+#include <type_traits>
+
+namespace ecckd {
+
+namespace {
+
+template <typename Real> struct PairOf;
+template <> struct PairOf<double> { using type = double2; };
+template <> struct PairOf<float> { using type = float2; };
+
+constexpr int kQCols = kQuadTileCols;   // columns per tile
+constexpr int kQNCW = 8;                // compute warps (4 columns each)
+constexpr int kQNI = 4;                 // index warps
+constexpr int kQNH = 4;                 // helper warpgroup: store warp + 3 Planck (LW) / source (SW) warps
+constexpr int kQWarps = kQNCW + kQNI + kQNH;
+constexpr int kNegFlag = 0x10000;       // key.x: upside-down layer whose negative-factor gases contribute (:143-149,233-238)
+
+// One layer of the record ring: structure-of-arrays over the 32 columns of the tile, so that the index warps
+// (lanes = columns) write and the compute warps (4 columns per warp) read without bank conflicts.
+template <typename Real, int NV> struct alignas(16) QRec {
+    using P = typename PairOf<Real>::type;
+    P c01[kQCols], c23[kQCols];   // tw0*pw0, tw0*pw1 | tw1*pw0, tw1*pw1
+    P lut[kQCols];                // LUT gas: weight (0 when it does not contribute), vmr_weight1
+    P w[(NV + 2) / 2][kQCols];    // weights: mixed table, varying gases 1..NV (0 when clamped away)
+    P aux[kQCols];                // simple_weight (SW: moles_per_layer; upside-down layers), unused
+    int2 key[kQCols];             // x: bilinear corner offset | kNegFlag; y: LUT corner offset
+};
+
+template <typename T> __device__ __forceinline__ T make_pair_(double a, double b);
+template <> __device__ __forceinline__ double2 make_pair_<double2>(double a, double b) { return make_double2(a, b); }
+template <> __device__ __forceinline__ float2 make_pair_<float2>(double a, double b) { return make_float2((float)a, (float)b); }
+
+// predicated loads of four cached rows (corners C00 C10 C01 C11 of one table slot), four g-points per row, written
+// straight into the cache registers (tied operands: nothing waits for the data until it is used one layer later)
+__device__ __forceinline__ void ld_rows_if(double (&r)[4][4], const double *p, bool pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %17, 0;\n\t"
+        "@q ld.global.nc.v2.f64 {%0, %1}, [%16];\n\t@q ld.global.nc.v2.f64 {%2, %3}, [%16+16];\n\t"
+        "@q ld.global.nc.v2.f64 {%4, %5}, [%16+%18];\n\t@q ld.global.nc.v2.f64 {%6, %7}, [%16+%18+16];\n\t"
+        "@q ld.global.nc.v2.f64 {%8, %9}, [%16+%19];\n\t@q ld.global.nc.v2.f64 {%10, %11}, [%16+%19+16];\n\t"
+        "@q ld.global.nc.v2.f64 {%12, %13}, [%16+%20];\n\t@q ld.global.nc.v2.f64 {%14, %15}, [%16+%20+16];\n\t}"
+        : "+d"(r[0][0]), "+d"(r[0][1]), "+d"(r[0][2]), "+d"(r[0][3]), "+d"(r[1][0]), "+d"(r[1][1]), "+d"(r[1][2]), "+d"(r[1][3]),
+          "+d"(r[2][0]), "+d"(r[2][1]), "+d"(r[2][2]), "+d"(r[2][3]), "+d"(r[3][0]), "+d"(r[3][1]), "+d"(r[3][2]), "+d"(r[3][3])
+        : "l"(p), "r"((int)pred), "n"(kC10 * 8), "n"(kC01 * 8), "n"(kC11 * 8));
+}
+__device__ __forceinline__ void ld_rows_if(float (&r)[4][4], const float *p, bool pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %17, 0;\n\t"
+        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%16];\n\t"
+        "@q ld.global.nc.v4.f32 {%4, %5, %6, %7}, [%16+%18];\n\t"
+        "@q ld.global.nc.v4.f32 {%8, %9, %10, %11}, [%16+%19];\n\t"
+        "@q ld.global.nc.v4.f32 {%12, %13, %14, %15}, [%16+%20];\n\t}"
+        : "+f"(r[0][0]), "+f"(r[0][1]), "+f"(r[0][2]), "+f"(r[0][3]), "+f"(r[1][0]), "+f"(r[1][1]), "+f"(r[1][2]), "+f"(r[1][3]),
+          "+f"(r[2][0]), "+f"(r[2][1]), "+f"(r[2][2]), "+f"(r[2][3]), "+f"(r[3][0]), "+f"(r[3][1]), "+f"(r[3][2]), "+f"(r[3][3])
+        : "l"(p), "r"((int)pred), "n"(kC10 * 4), "n"(kC01 * 4), "n"(kC11 * 4));
+}
+
+template <typename P> __device__ __forceinline__ P lds_pair(unsigned addr);
+template <> __device__ __forceinline__ double2 lds_pair<double2>(unsigned addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ float2 lds_pair<float2>(unsigned addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds_int2(unsigned addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+template <typename Real> __device__ __forceinline__ void sts_(unsigned addr, Real v);
+template <> __device__ __forceinline__ void sts_<double>(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+}  // namespace
+
+// Real   double | float (arithmetic and I/O type; index arithmetic is always double)
+// NV     register-cached varying bilinear gases (1 or 3); the call's nvar may be smaller
+// LUT32  cache the look-up-table rows as fp32 (exact: the files are f4) and widen them in the FMA chain
+// R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH>
+__global__ void __launch_bounds__(kQWarps * 32, 1)
+quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
+            const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
+{
+    using RecT = QRec<Real, NV>;
+    using P = typename PairOf<Real>::type;
+    using LutT = typename std::conditional<LUT32, float, Real>::type;
+    constexpr int NOUT = SW ? 2 : 1;                       // staged outputs: tau (+ ssa)
+    constexpr int NBOX = sizeof(Real) == 8 ? 2 : 1;        // 128-byte rows: 16 fp64 or 32 fp32 columns per TMA box
+    constexpr int BOXB = 32 * 128;                         // bytes of one box in shared memory: 32 g-points x 128 bytes
+    constexpr int TILEB = NBOX * BOXB;                     // one staged output of one layer
+    constexpr int NPW = kQNH - 1;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *stage = smem_raw;                                           // [NBUF][NOUT][TILEB]  (1024-byte aligned)
+    unsigned char *zero_tile = stage + (size_t)NBUF * NOUT * TILEB;            // SW: source of the g = 0 plane
+    RecT *recs = reinterpret_cast<RecT *>(zero_tile + (SW ? BOXB : 0));        // [R]
+    unsigned long long *tile_full = reinterpret_cast<unsigned long long *>(recs + R);
+    unsigned long long *tile_empty = tile_full + NBUF;
+    unsigned long long *rec_full = tile_empty + NBUF;
+    unsigned long long *rec_empty = rec_full + R;
+    float2 *spl2 = reinterpret_cast<float2 *>(rec_empty + R);                  // LW: Planck LUT of this g-group, [g][row] (row, row+1)
+
+    // logical warp order [compute | index | store | helpers]; hardware warp ids run the other way round because the
+    // issue arbiter prefers the highest warp id: the compute warps get priority over the throughput-oriented helpers
+    const int warp = kQWarps - 1 - (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int ncol = a.ncol, nlay = a.nlay, ngpt = m.ngpt;
+    const int grp = blockIdx.y, g0 = grp * kGP;
+    const int ntile_all = (ncol + kQCols - 1) / kQCols;
+    const int nslot = (ntile_all - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this block: b, b + grid, ...
+    const int S = nslot * nlay;                                                             // stream positions of this block
+    const size_t pitch = (size_t)ncol, plane = (size_t)ncol * nlay;
+    const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
+    const int nvar = cg.nvar;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&tile_full[b], kQNCW); mbar_init(&tile_empty[b], 1); }
+        for (int q = 0; q < R; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], kQNCW); }
+    }
+    if (!SW) {   // each entry holds the row AND its upper neighbour: one 8-byte LDS fetches both interpolation operands
+        const int np_ = m.nplanck;
+        for (int q = threadIdx.x; q < np_ * kGP; q += blockDim.x) {
+            const int row = q / kGP, gl = q % kGP;
+            const bool gok = g0 + gl < ngpt;
+            const float p0 = gok ? m.planck32[(size_t)row * ngpt + g0 + gl] : 0.0f;
+            const float p1 = (gok && row + 1 < np_) ? m.planck32[(size_t)(row + 1) * ngpt + g0 + gl] : 0.0f;
+            spl2[gl * np_ + row] = make_float2(p0, p1);
+        }
+    } else {
+        for (int q = threadIdx.x; q < BOXB / 4; q += blockDim.x) reinterpret_cast<float *>(zero_tile)[q] = 0.0f;
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    // ================================ helper warpgroup ================================
+    if (warp >= kQNCW + kQNI) {
+        reg_dec<RH>();
+        const int hw = warp - (kQNCW + kQNI);
+        if (hw == 0) {
+            // ---- store warp: staging tiles -> cp.async.bulk.tensor stores ----
+            if (lane == 0) {
+                int b = 0, par = 0, ts = 0, j = 0;
+                for (int s = 0; s < S; ++s) {
+                    const int col0 = ((int)blockIdx.x + ts * (int)gridDim.x) * kQCols;
+                    mbar_wait_relaxed(&tile_full[b], par, kStoreNap);
+                    const unsigned char *sb = stage + (size_t)b * NOUT * TILEB;
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o)
+                        if (a.out[o]) {
+#pragma unroll
+                            for (int h = 0; h < NBOX; ++h)
+                                if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[o], sb + o * TILEB + h * BOXB, col0 + 16 * h, j, g0);
+                        }
+                    if (SW && a.out[2]) {
+#pragma unroll
+                        for (int h = 0; h < NBOX; ++h)
+                            if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[2], zero_tile, col0 + 16 * h, j, g0);   // g = 0  :460
+                    }
+                    tma_commit();
+                    tma_wait_read<0>();                  // the tile has been read out of shared memory: hand it back
+                    mbar_arrive(&tile_empty[b]);
+                    if (++b == NBUF) { b = 0; par ^= 1; }
+                    if (++j == nlay) { j = 0; ++ts; }
+                }
+                tma_wait_all<0>();
+            }
+            return;
+        }
+        const int pw = hw - 1;
+        const int ng = min(kGP, ngpt - g0);
+        if (SW) {
+            // ---- toa_src(:, g) = solar_irradiance(g)   :468-472 (lanes = columns) ----
+            if (a.out2d) {
+                for (int ts = pw; ts < nslot; ts += NPW) {
+                    const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+                    if (cc < ncol)
+                        for (int gq = 0; gq < ng; ++gq) a.out2d[cc + (long long)ncol * (g0 + gq)] = (Real)m.solar[g0 + gq];
+                }
+            }
+            return;
+        }
+        // ---- Planck warps (LW): lanes = columns, a unit is one level of one tile ----
+        {
+            if (ECCKD_DBG(64)) return;
+            const int S_ = m.nplanck;
+            const bool has_lev = a.tlev != nullptr;
+            const int nlevu = has_lev ? nlay + 1 : nlay;          // levels 0..nlay carry a value when tlev is present
+            const int nunit = nslot * nlevu;
+            auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
+                const int ts = u / nlevu;
+                j = u - ts * nlevu;
+                const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+                c_ok = cc < ncol;
+                colp = min(cc, (long long)ncol - 1);
+            };
+            // software pipeline: the temperatures of the next unit are fetched before the g-loop of the current one
+            auto fetch = [&](int u, double &tl, double &tv) {
+                int j; long long colp; bool c_ok;
+                place(u, j, colp, c_ok);
+                tl = (double)a.tlay[colp + (long long)ncol * min(j, nlay - 1)];
+                tv = 0.0;
+                if (has_lev) tv = (double)a.tlev[colp + (long long)ncol * min(j, nlay)];
+            };
+            double tl_n = 0.0, tv_n = 0.0;
+            if (pw < nunit) fetch(pw, tl_n, tv_n);
+            const size_t plane_b = plane * sizeof(Real);
+            for (int u = pw; u < nunit; u += NPW) {
+                int j; long long colp; bool c_ok;
+                place(u, j, colp, c_ok);
+                const bool ok_lay = c_ok && j < nlay;                       // lay_source(:,j), lev_source_dec(:,j)
+                const bool ok_inc = c_ok && has_lev && j >= 1 && j <= nlay; // lev_source_inc(:,j-1)
+                const double tl = tl_n, tv = tv_n;
+                if (u + NPW < nunit) fetch(u + NPW, tl_n, tv_n);
+                double a0, a1;
+                int it = planck_index(m, tl, a0, a1);
+                const float2 *tl_p = spl2 + (max(it, 1) - 1);
+                const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
+                const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
+                char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
+                int so = 0;
+                if (has_lev) {
+                    it = planck_index(m, tv, a0, a1);
+                    const float2 *tv_p = spl2 + (max(it, 1) - 1);
+                    const Real v0 = (Real)__ddiv_rn(a0, m.pi), v1 = (Real)__ddiv_rn(a1, m.pi);
+                    char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
+                    char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
+#pragma unroll 4
+                    for (int gq = 0; gq < ng; ++gq, so += S_, p_lay += plane_b, p_dec += plane_b, p_inc += plane_b) {
+                        const float2 pl = tl_p[so], pv = tv_p[so];
+                        const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
+                        const Real vv = fma_(v1, (Real)pv.y, mul_(v0, (Real)pv.x));      // B(tlev(:,j))
+                        stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay);
+                        stcs_if(reinterpret_cast<Real *>(p_dec), vv, ok_lay);            // lev_source_dec(:,j)   :424
+                        stcs_if(reinterpret_cast<Real *>(p_inc), vv, ok_inc);            // lev_source_inc(:,j-1) :423
+                    }
+                } else {
+#pragma unroll 4
+                    for (int gq = 0; gq < ng; ++gq, so += S_, p_lay += plane_b) {
+                        const float2 pl = tl_p[so];
+                        const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
+                        stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay);
+                    }
+                }
+            }
+            if (a.out2d) {                                 // sfc_source(:, g) = B(tsfc)   :408-412
+                for (int ts = pw; ts < nslot; ts += NPW) {
+                    const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+                    const long long colp = min(cc, (long long)ncol - 1);
+                    double a0, a1;
+                    const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
+                    const int r = max(it, 1) - 1;
+                    const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
+                    if (cc < ncol)
+                        for (int gq = 0; gq < ng; ++gq) {
+                            const float2 ps = spl2[gq * S_ + r];
+                            a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, (Real)ps.y, mul_(s0, (Real)ps.x));
+                        }
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================ index warps =====================================
+    if (warp >= kQNCW) {
+        reg_dec<RI>();
+        const int iw = warp - kQNCW;
+        int ts = 0, j = iw;                                    // position s = ts * nlay + j
+        while (j >= nlay) { j -= nlay; ++ts; }
+        int slot = iw % R, n = iw / R;                          // ring slot of s and how often it has been used before
+        for (int s = iw; s < S; s += kQNI) {
+            const long long col = min((long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane, (long long)ncol - 1);
+            // (tail tiles recompute the last column; never stored)
+            P c01, c23, lutw, wv[(NV + 2) / 2], aux;
+            int2 key;
+            {
+                const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
+                const double tl = (double)a.tlay[col + (long long)ncol * j];
+                const CellIndex ci = cell_index(m, pu, pl, tl);
+                const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
+                c01 = make_pair_<P>(__dmul_rn(tw0, pw0), __dmul_rn(tw0, ci.pw1));
+                c23 = make_pair_<P>(__dmul_rn(ci.tw1, pw0), __dmul_rn(ci.tw1, ci.pw1));
+                const int ip = ci.ip0 - 1, it = ci.it0 - 1;
+                // Tables are >= 0 (checked at model create), so od < 0 <=> weight < 0: the per-g clamp (:233-238)
+                // becomes "the gas contributes nothing when its weight is negative" -- its weight is stored as 0,
+                // which leaves tau unchanged bit for bit (fma(0, finite, tau) == tau); NaN weights propagate.
+                const bool up = ci.sw < 0.0;
+                double W[NV + 1];
+                W[0] = (has_mix && !up) ? ci.sw : 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    double wd = 0.0;
+                    if (v < nvar) {
+                        const GasRef &gr = cg.g[cg.var_gas[v]];
+                        wd = gas_weight(gr, ci.sw, load_vmr<Real>(gr, col, j));
+                        if (wd < 0.0) wd = 0.0;
+                    }
+                    W[v + 1] = wd;
+                }
+#pragma unroll
+                for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = make_pair_<P>(W[2 * v], 2 * v + 1 <= NV ? W[2 * v + 1] : 0.0);
+                aux = make_pair_<P>(ci.sw, 0.0);
+                key.x = (ip * kNTP + it) * kGP | ((has_mix && up) ? kNegFlag : 0);
+                key.y = 0;
+                lutw = make_pair_<P>(0.0, 0.0);
+                if (has_lut) {
+                    const GasRef &gr = cg.g[cg.lut];
+                    const double vmr = load_vmr<Real>(gr, col, j);
+                    double v1;
+                    const int iv = vmr_index(gr, vmr, v1) - 1;
+                    key.y = ((iv * kNPP + ip) * kNTP + it) * kGP;
+                    double wd = gas_weight(gr, ci.sw, vmr);
+                    if (wd < 0.0) wd = 0.0;
+                    lutw = make_pair_<P>(wd, v1);
+                }
+            }
+            if (n >= 1) mbar_wait_relaxed(&rec_empty[slot], (n - 1) & 1, kIndexNap);
+            RecT &rc = recs[slot];
+            rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane] = key;
+#pragma unroll
+            for (int v = 0; v < (NV + 2) / 2; ++v) rc.w[v][lane] = wv[v];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rec_full[slot]);
+            j += kQNI; while (j >= nlay) { j -= nlay; ++ts; }
+            slot += kQNI; while (slot >= R) { slot -= R; ++n; }
+        }
+        return;
+    }
+
+    // ================================ compute warps ===================================
+    reg_inc<RC>();
+    const int cw = lane >> 3, q = lane & 7;            // column of the warp's quad, lane of the column
+    const int ct = 4 * warp + cw;                      // column of the tile
+    const int ngroups = gridDim.y;
+    // table pointers of this lane: 4 consecutive (permuted) positions = g-points q, q+8, q+16, q+24
+    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + 4 * q;
+    const LutT *wlut = (LUT32 ? reinterpret_cast<const LutT *>(m.wlut32) : reinterpret_cast<const LutT *>(TableOf<Real>::wlut(m))) +
+                       (size_t)grp * m.nv_lut * kSlab + 4 * q;
+    const Real *wmix = mixtab + (size_t)grp * kSlab + 4 * q;     // negative-sign copy at + ngroups*kSlab
+    const float *wvar[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) wvar[v] = wbil + (v < nvar ? cg.var_off[v] : 0);
+
+    Real km[4][4];            // mixed table      [corner][g]
+    float kb[NV][4][4];       // varying gases (fp32 rows, exact; widened in the FMA chain)
+    LutT kh[2][4][4];         // look-up-table gas, mole fractions iv0 and iv0 + 1
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            km[r][i] = 0; kh[0][r][i] = 0; kh[1][r][i] = 0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) kb[v][r][i] = 0;
+        }
+    int cur_pk = -1, cur_hk = -1;
+    Real sigma[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sigma[i] = SW ? (Real)m.rayleigh[min(g0 + q + 8 * i, ngpt - 1)] : (Real)0;
+
+    // (re)load the register cache for corner offsets (pkoff, hkoff); every load is predicated on "this column's key
+    // moved", so the four columns of the warp refill independently without divergence
+    auto refill = [&](int pkoff, int hkoff) {
+        const bool pb = pkoff != cur_pk, pl = has_lut && hkoff != cur_hk;
+        if (!ECCKD_DBG(8)) {
+            ld_rows_if(km, wmix + pkoff, pb && has_mix);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, pb && v < nvar);
+            ld_rows_if(kh[0], wlut + hkoff, pl);
+            ld_rows_if(kh[1], wlut + hkoff + kSlab, pl);
+        }
+        cur_pk = pkoff; cur_hk = hkoff;
+    };
+
+    // staging address of this lane's first value (g-point q): row = g, 16-byte chunks XOR-swizzled with (row & 7) = q
+    // exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out; value i (g-point q + 8 i) is 8 rows = 1024 bytes further
+    unsigned st_off;
+    if (sizeof(Real) == 8) {
+        const int col16 = 4 * (warp & 3) + cw;
+        st_off = (warp >> 2) * BOXB + q * 128 + (((col16 >> 1) ^ q) << 4) + (col16 & 1) * 8;
+    } else {
+        st_off = q * 128 + ((warp ^ q) << 4) + cw * 4;
+    }
+    unsigned stage_a = smem_u32(stage) + st_off;
+    unsigned a_tfull = smem_u32(tile_full), a_tempty = smem_u32(tile_empty);
+    unsigned a_rfull = smem_u32(rec_full), a_rempty = smem_u32(rec_empty);
+    // record fields of this lane's column, as shared-window addresses relative to the ring slot
+    constexpr unsigned PB = sizeof(P), RB = sizeof(RecT);
+    constexpr unsigned O_C01 = 0, O_C23 = kQCols * PB, O_LUT = 2 * kQCols * PB, O_W = 3 * kQCols * PB,
+                       O_AUX = (3 + (NV + 2) / 2) * kQCols * PB, O_KEY = (4 + (NV + 2) / 2) * kQCols * PB;
+    static_assert(O_KEY + kQCols * 8 == RB, "record layout");
+    unsigned rec_a = smem_u32(recs) + ct * PB, key_a = smem_u32(recs) + O_KEY + ct * 8;
+    // loop invariants are pinned in registers: otherwise they are rematerialised from kernel parameters and special
+    // registers in every iteration (measured in round 1, and visible in the SASS)
+    keep(stage_a); keep(a_tfull); keep(a_tempty); keep(a_rfull); keep(a_rempty); keep(rec_a); keep(key_a);
+    keep(wmix); keep(wlut);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) keep(wvar[v]);
+
+    if (S > 0) {
+        mbar_wait_a(a_rfull, 0);
+        int2 key = lds_int2(key_a);
+        refill(key.x & 0xffff, key.y);
+        int slot = 0, rpar = 0, b = 0, tpar = 1;       // tpar: parity to wait for on tile_empty (the phase before the
+                                                       // initial one counts as complete, so the first pass never blocks)
+        for (int s = 0; s < S; ++s) {
+            const unsigned ra = rec_a + slot * RB;
+            const P c01 = lds_pair<P>(ra + O_C01), c23 = lds_pair<P>(ra + O_C23), lw = lds_pair<P>(ra + O_LUT);
+            P wv[(NV + 2) / 2];
+#pragma unroll
+            for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
+            const Real c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
+            const Real omv = add_((Real)1, -lw.y);
+            Real tau[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const Real b0 = bil4(c0, c1, c2, c3, kh[0][0][i], kh[0][1][i], kh[0][2][i], kh[0][3][i]);
+                const Real b1 = bil4(c0, c1, c2, c3, kh[1][0][i], kh[1][1][i], kh[1][2][i], kh[1][3][i]);
+                const Real bm = bil4(c0, c1, c2, c3, km[0][i], km[1][i], km[2][i], km[3][i]);
+                // (1-v1)*b0 + v1*b1, not b0 + v1*(b1-b0): that cancels when b1 << b0
+                Real t = mul_(lw.x, fma_(lw.y, b1, mul_(omv, b0)));
+                t = fma_(wv[0].x, bm, t);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const Real bv = bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
+                    const Real wgt = ((v + 1) & 1) ? wv[(v + 1) >> 1].y : wv[(v + 1) >> 1].x;
+                    t = fma_(wgt, bv, t);
+                }
+                tau[i] = t;
+            }
+            if (key.x & kNegFlag) {   // upside-down layer: the negative-factor gases give positive optical depth
+                const Real *k = wmix + (size_t)ngroups * kSlab + (key.x & 0xffff);
+                const Real swt = lds_pair<P>(ra + O_AUX).x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tau[i] = fma_(swt, bil4(c0, c1, c2, c3, k[kC00 + i], k[kC10 + i], k[kC01 + i], k[kC11 + i]), tau[i]);
+            }
+            // the cache has been read: fetch the next position's corners under the rest of this layer's work
+            const int nslot_r = slot + 1 == R ? 0 : slot + 1;
+            if (s + 1 < S) {
+                mbar_wait_a(a_rfull + nslot_r * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
+                key = lds_int2(key_a + nslot_r * RB);
+                refill(key.x & 0xffff, key.y);
+            }
+            Real ssa[4];
+            if (SW) {
+                const Real swt = lds_pair<P>(ra + O_AUX).x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const Real ray = mul_(swt, sigma[i]);             // :313-316 (moles_per_layer == simple_weight, same product)
+                    tau[i] = add_(tau[i], ray);                       // :456
+                    ssa[i] = div_fast(ray, tau[i]);                   // :459
+                }
+            }
+            mbar_wait_a(a_tempty + b * 8, tpar);
+            const unsigned sa = stage_a + b * (NOUT * TILEB);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sts_<Real>(sa + i * 1024, tau[i]);
+                if (SW) sts_<Real>(sa + TILEB + i * 1024, ssa[i]);
+            }
+            fence_proxy_async_smem();          // generic-proxy writes -> visible to the async (TMA) proxy
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_a(a_tfull + b * 8);
+                mbar_arrive_a(a_rempty + slot * 8);
+            }
+            if (++b == NBUF) { b = 0; tpar ^= 1; }
+            slot = nslot_r;
+            if (slot == 0) rpar ^= 1;
+        }
+    }
+}
+
+// ============================================================================
+// launcher
+// ============================================================================
+// 3-D map of an (ncol, nlay, ngpt) output, box = 128 bytes of columns x 1 layer x 32 g-points, 128-byte swizzle
+template <typename Real> static bool encode_quad_map(CUtensorMap *map, Real *ptr, int ncol, int nlay, int ngpt)
+{
+    auto enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t w = sizeof(Real);
+    const cuuint64_t gdim[3] = {(cuuint64_t)ncol, (cuuint64_t)nlay, (cuuint64_t)ngpt};
+    const cuuint64_t gstr[2] = {(cuuint64_t)ncol * w, (cuuint64_t)ncol * nlay * w};
+    const cuuint32_t box[3] = {(cuuint32_t)(128 / w), 1, 32}, estr[3] = {1, 1, 1};
+    return enc(map, w == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArgs<Real> &a)
+{
+    if (cg.nvar > kQuadMaxVar) return false;
+    if ((size_t)a.ncol * sizeof(Real) % 16) return false;            // tensor-map strides are multiples of 16 bytes
+    for (int o = 0; o < 3; ++o) if (a.out[o] && (reinterpret_cast<uintptr_t>(a.out[o]) & 15)) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64>
+static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
+{
+    constexpr int NOUT = SW ? 2 : 1;
+    constexpr int TILEB = (sizeof(Real) == 8 ? 2 : 1) * 32 * 128;
+    TmaMaps maps{};
+    for (int o = 0; o < (SW ? 3 : 1); ++o)
+        if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)NBUF * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV>) * R +
+                        (2 * NBUF + 2 * R) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int ntile = (a.ncol + kQCols - 1) / kQCols;
+    int blocks = ntile < sms ? ntile : sms;
+    if (blocks < 1) blocks = 1;
+#ifdef ECCKD_TUNE
+    if (getenv("ECCKD_BLOCKS")) blocks = std::min(ntile, atoi(getenv("ECCKD_BLOCKS")));
+#endif
+    dim3 grid((unsigned)blocks, (unsigned)((m.ngpt + kGP - 1) / kGP));
+    kern<<<grid, kQWarps * 32, smem, s>>>(m, cg, a, mix, maps);
+    return cudaGetLastError();
+}
+
+template <typename Real, bool SW>
+cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
+{
+#ifdef ECCKD_TUNE
+    // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
+    static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
+    if (cg.nvar <= 1) {
+        if (v == 1) return launch_quad_t<Real, SW, 1, false, 8, 4>(m, cg, a, mix, sms, s);
+        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 8>(m, cg, a, mix, sms, s);
+        if (v == 3) return launch_quad_t<Real, SW, 1, false, 32, 6>(m, cg, a, mix, sms, s);
+        if (v == 4) return launch_quad_t<Real, SW, 1, true, 16, 6>(m, cg, a, mix, sms, s);
+        if (v == 5) return launch_quad_t<Real, SW, 1, true, 8, 4>(m, cg, a, mix, sms, s);
+        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 80>(m, cg, a, mix, sms, s);
+    }
+#endif
+    if (cg.nvar <= 1) return launch_quad_t<Real, SW, 1, false, 16, 6>(m, cg, a, mix, sms, s);
+    return launch_quad_t<Real, SW, kQuadMaxVar, false, 16, 6>(m, cg, a, mix, sms, s);
+}
+
+#define ECCKD_QUAD_INST(Real)                                                                                                   \
+    template bool quad_eligible<Real>(const CallGases &, const KernelArgs<Real> &);                                              \
+    template cudaError_t launch_quad<Real, false>(const DevModel &, const CallGases &, const KernelArgs<Real> &, const Real *, int, cudaStream_t); \
+    template cudaError_t launch_quad<Real, true>(const DevModel &, const CallGases &, const KernelArgs<Real> &, const Real *, int, cudaStream_t);
+ECCKD_QUAD_INST(double)
+ECCKD_QUAD_INST(float)
+
+}  // namespace ecckd

@@ -13,7 +13,7 @@ ERRLEN = 128
 NAME_LEN = 32
 MAX_GASES = 16
 OK, ERR_ARG, ERR_CUDA, ERR_REFERENCE, ERR_IO = 0, 1, 2, 3, 4
-KERNEL_AUTO, KERNEL_WALK, KERNEL_GENERIC = 0, 1, 2
+KERNEL_AUTO, KERNEL_WALK, KERNEL_GENERIC, KERNEL_QUAD, KERNEL_COLWALK = 0, 1, 2, 3, 4
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libecckd_b200.so")

@@ -48,15 +48,22 @@ def c_oracles(ck_models):
 
 
 def rel_err(a, b):
-    """max |a-b| / |b| with exact zeros (and bit-equal values) counting as 0."""
+    """max |a-b| / |b| with exact zeros (and bit-equal values) counting as 0.
+    A NaN on one side only is an infinite error (a kernel that writes NaN where the
+    oracle is finite must fail); NaN on both sides at the same element counts as equal."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return float("inf")
     if a.size == 0:
         return 0.0
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    if np.any(nan_a != nan_b):
+        return float("inf")
     den = np.maximum(np.abs(b), np.finfo(np.float64).tiny)
     with np.errstate(invalid="ignore"):
-        e = np.where((a == b) | (np.isnan(a) & np.isnan(b)), 0.0, np.abs(a - b) / den)
-    return float(np.nanmax(e)) if not np.all(np.isnan(e)) else float("nan")
+        e = np.where((a == b) | (nan_a & nan_b), 0.0, np.abs(a - b) / den)
+    return float(np.max(e))
 
 
 def atm_numpy(atm):

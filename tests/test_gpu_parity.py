@@ -16,7 +16,9 @@ from conftest import FILES, atm_numpy, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float64: 1e-12, torch.float32: 1e-5}
-KERNELS = {"walk": ecckd_b200.KERNEL_WALK, "generic": ecckd_b200.KERNEL_GENERIC}
+# "walk" = the product path (quad kernel when the call admits TMA tensor maps, else the one-column-per-warp kernel);
+# "colwalk" forces the latter (the fallback for odd column counts) also where the quad kernel would run
+KERNELS = {"walk": ecckd_b200.KERNEL_WALK, "colwalk": ecckd_b200.KERNEL_COLWALK, "generic": ecckd_b200.KERNEL_GENERIC}
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -132,7 +134,7 @@ def test_planck_indices_bit_exact(dev, gpu_models, c_oracles):
 
 # ---- shapes: empty, single, ragged ----------------------------------------------------------------
 @pytest.mark.parametrize("kernel", list(KERNELS))
-@pytest.mark.parametrize("ncol,nlay", [(1, 1), (1, 137), (17, 33), (16, 32), (15, 31), (33, 64), (3, 65)])
+@pytest.mark.parametrize("ncol,nlay", [(1, 1), (1, 137), (17, 33), (16, 32), (15, 31), (33, 64), (3, 65), (2, 3), (34, 20), (64, 137), (30, 5)])
 def test_ragged_shapes(ncol, nlay, kernel, dev, gpu_models, ck_models, c_oracles):
     for key in ("lw_rrtmgp", "sw_wide"):      # 36 g-points = two g-groups, 27 = a partial one
         inp = atm_numpy(synthetic.make_atmosphere(ncol, nlay, col0=1000))
@@ -325,6 +327,37 @@ def test_large_block_properties(dtype, dev, gpu_models, ck_models, c_oracles):
         o2 = go.gas_optics(None, sub(atm.plev), sub(atm.tlay), atm.tsfc[:4096][perm].contiguous() if lw else None, gl2,
                            tlev=sub(atm.tlev) if lw else None)
         assert torch.equal(o2["tau"], out["tau"][:4096][perm])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("ncol,nlay", [(4, 1), (32, 7), (36, 137), (5000, 9), (4736 + 32, 3)])
+def test_quad_kernel_equals_column_walk_bitwise(ncol, nlay, dtype, dev, gpu_models):
+    """The quad kernel (4 columns per warp, TMA stores) and the one-column-per-warp kernel run the same explicitly
+    rounded arithmetic per g-point: every output agrees bit for bit, for all three ck files, also with several
+    tiles per persistent block (5000 columns = 157 tiles > 148 SMs)."""
+    atm = synthetic.make_atmosphere(ncol, nlay, device=dev)
+    if dtype == torch.float32:
+        atm = atm.astype(dtype)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    for key, go in gpu_models.items():
+        lw = go.source_is_internal()
+        gases = ecckd_b200.PreparedGases(atm.gas_list(), ncol, nlay, npdt, dev)
+        call = lambda kern: go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc if lw else None, gases,
+                                          tlev=atm.tlev if lw else None, kernel=kern)
+        q, w = call(ecckd_b200.KERNEL_QUAD), call(ecckd_b200.KERNEL_COLWALK)
+        torch.cuda.synchronize()
+        for k in q:
+            assert torch.equal(q[k], w[k]), f"{key} {k}: quad and column-walk kernels differ"
+
+
+def test_quad_kernel_refuses_what_it_cannot_map(dev, gpu_models):
+    """Odd fp64 column counts have no 16-byte-aligned layer pitch: no tensor map, so QUAD is an argument error and
+    AUTO / WALK fall back to the column-walk kernel."""
+    atm = synthetic.make_atmosphere(33, 5, device=dev)
+    go = gpu_models["lw_fsck"]
+    with pytest.raises(ecckd_b200.EcckdError):
+        go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc, atm.gas_list(), tlev=atm.tlev, kernel=ecckd_b200.KERNEL_QUAD)
+    go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc, atm.gas_list(), tlev=atm.tlev, kernel=ecckd_b200.KERNEL_WALK)
 
 
 @pytest.mark.parametrize("ncol", [18922, 18921], ids=["even-tma", "odd-writer"])
