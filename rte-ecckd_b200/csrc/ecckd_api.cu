@@ -504,7 +504,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
                     if (g >= ng) continue;
                     for (int ip = 0; ip < np; ++ip)
                         for (int it = 0; it < nt; ++it) {
-                            const size_t cell = ((size_t)ip * kNTP + it) * kGP + walk_pos(ln);
+                            const size_t cell = ((size_t)ip * kNTP + it) * kGP + walk_pos64(ln);
                             const size_t src = (size_t)g + (size_t)ng * (ip + (size_t)np * it);
                             for (int q = 0; q < nslot; ++q)
                                 wbil64[((size_t)grp * nslot + q) * kSlab + cell] = k64[slot_off[q] + src];
@@ -516,7 +516,12 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         }
         M->nslot_ = nslot; M->nv_lut_ = lut_gas >= 0 ? M->nv[lut_gas] : 0;
     }
-    auto narrow = [](const std::vector<double> &v) { std::vector<float> f(v.size()); for (size_t q = 0; q < v.size(); ++q) f[q] = (float)v[q]; return f; };
+    // fp32 copies: rows re-permuted from the 8-byte to the 4-byte layout (see walk_pos32 / walk_pos64)
+    auto narrow = [](const std::vector<double> &v) {
+        std::vector<float> f(v.size());
+        for (size_t q = 0; q < v.size(); ++q) f[(q & ~size_t(kGP - 1)) + walk_pos32(walk_inv64((int)(q & (kGP - 1))))] = (float)v[q];
+        return f;
+    };
     const std::vector<float> wbil32 = narrow(wbil64), wlut32 = narrow(wlut64);
     std::vector<double> tbase(t->temperature, t->temperature + t->npress);               // temperature(:,1)
     std::vector<double> ray, sol;

@@ -23,9 +23,17 @@ constexpr int kNTP = 8;                    // padded temperature extent   (ntemp
 constexpr int kNPP = 64;                   // padded pressure extent      (npress <= 64)
 constexpr int kSlab = kNPP * kNTP * kGP;   // elements of one (slot | mole-fraction) slab
 // Position of g-point l (0..31) of a group inside a 32-element table row.  Rows are stored permuted so that the four
-// g-points {q, q+8, q+16, q+24} of one thread of the quad kernel (8 lanes per column, 4 g-points per lane) are one
-// 16/32-byte vector, while their rows in the 128-byte-swizzled staging tile (swizzle key = g & 7 = q) stay conflict-free.
-__host__ __device__ constexpr int walk_pos(int l) { return ((l & 7) << 2) | (l >> 3); }
+// g-points {q, q+8, q+16, q+24} of one thread of the quad kernel (8 lanes per column, 4 g-points per lane) come from
+// 16-byte vector loads that are contiguous across the 8 lanes, while their rows in the 128-byte-swizzled staging
+// tile (swizzle key = g & 7 = q) stay conflict-free:
+//   4-byte rows (128 B): one 16-byte load per lane          -> [q][i]          i = g >> 3, q = g & 7
+//   8-byte rows (256 B): two 16-byte loads per lane, each a contiguous 128-byte half row -> [i >> 1][q][i & 1]
+__host__ __device__ constexpr int walk_pos32(int l) { return ((l & 7) << 2) | (l >> 3); }
+__host__ __device__ constexpr int walk_pos64(int l) { return ((l >> 4) << 4) | ((l & 7) << 1) | ((l >> 3) & 1); }
+__host__ __device__ constexpr int walk_inv32(int p) { return (p >> 2) | ((p & 3) << 3); }
+__host__ __device__ constexpr int walk_inv64(int p) { return ((p >> 1) & 7) | ((((p >> 4) << 1) | (p & 1)) << 3); }
+template <typename T> __host__ __device__ constexpr int walk_pos(int l) { return sizeof(T) == 8 ? walk_pos64(l) : walk_pos32(l); }
+template <typename T> __host__ __device__ constexpr int walk_inv(int p) { return sizeof(T) == 8 ? walk_inv64(p) : walk_inv32(p); }
 
 enum Code : int { kNone = 0, kLinear = 1, kLut = 2, kRelLinear = 3 };  // :54-57
 

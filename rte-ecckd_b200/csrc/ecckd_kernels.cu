@@ -146,7 +146,9 @@ mix_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ngroups * kSlab) return;
     const int grp = e / kSlab, cell = e % kSlab;
-    const double *src = m.wbil64 + (size_t)grp * m.nslot * kSlab + cell;
+    // e is a position of the OUTPUT row layout (Real-wide rows); the fp64 source tables use the 8-byte layout
+    const int src_cell = (cell & ~(kGP - 1)) + walk_pos64(walk_inv<Real>(cell & (kGP - 1)));
+    const double *src = m.wbil64 + (size_t)grp * m.nslot * kSlab + src_cell;
     double plus = 0.0, minus = 0.0;
     for (int q = 0; q < cg.nmix; ++q) {
         const GasRef &gr = cg.g[cg.mix_gas[q]];
@@ -566,9 +568,9 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // LUT gas (eight values per layer) is cached at full width, because the conversion pipe (16 lanes/clk/SM) is
     // shared with the Planck warps and eight more F2F per layer measurably slow both; the per-call mixed table, a
     // sum of products, needs the full Real width anyway.
-    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + walk_pos(lane);
-    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + walk_pos(lane);
-    const Real *wmix = mixtab + (size_t)grp * kSlab + walk_pos(lane);          // negative-sign copy at + ngroups*kSlab
+    const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + walk_pos32(lane);
+    const Real *wlut = TableOf<Real>::wlut(m) + (size_t)grp * m.nv_lut * kSlab + walk_pos<Real>(lane);
+    const Real *wmix = mixtab + (size_t)grp * kSlab + walk_pos<Real>(lane);          // negative-sign copy at + ngroups*kSlab
     const float *wvar = wbil + (NB == 2 ? cg.var_off[0] : 0);       // NB == 2: the one varying gas
     if constexpr ((RF & 2) != 0) { keep(wvar); keep(wlut); keep(wmix); }
 
@@ -919,7 +921,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                 for (int o = 0; o < (SW ? 3 : 1); ++o)
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
-#ifdef ECCKD_TUNE
+#ifdef ECCKD_TUNE_WALK1
                     // tuning build: ECCKD_WALK_VARIANT selects an alternative instantiation (tools/tune.sh)
                     //   100 + RF      refill flavour RF at the default geometry
                     //   LW 1..5       2 / 4 / 6 / 8 Planck warps, 3 index warps      LW 6..8   ring of 4 / 8 / 16 tiles
@@ -962,7 +964,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                 }
             }
         }
-#ifdef ECCKD_TUNE
+#ifdef ECCKD_TUNE_WALK1
         if constexpr (!SW) {   // writer-warp path, longwave: 21..23 = 2 writer warps + 3 Planck warps with 2- / 4-layer tiles, 3 writer warps
             static const int v = getenv("ECCKD_WALK_VARIANT") ? atoi(getenv("ECCKD_WALK_VARIANT")) : 0;
             if (v == 21) return launch_walk_t<Real, SW, 2, 16, 2, 4, 4, 2, false, 1, 3, 0, 18>(m, cg, a, mix, s);

@@ -66,15 +66,17 @@ template <> __device__ __forceinline__ double2 make_pair_<double2>(double a, dou
 template <> __device__ __forceinline__ float2 make_pair_<float2>(double a, double b) { return make_float2((float)a, (float)b); }
 
 // predicated loads of four cached rows (corners C00 C10 C01 C11 of one table slot), four g-points per row, written
-// straight into the cache registers (tied operands: nothing waits for the data until it is used one layer later)
+// straight into the cache registers (tied operands: nothing waits for the data until it is used one layer later).
+// 8-byte rows: the lane's g-points {q, q+8} and {q+16, q+24} sit in the two 128-byte halves of the row (walk_pos64),
+// so each 16-byte load instruction reads contiguous memory across the 8 lanes of a column.
 __device__ __forceinline__ void ld_rows_if(double (&r)[4][4], const double *p, bool pred)
 {
     asm volatile(
         "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %17, 0;\n\t"
-        "@q ld.global.nc.v2.f64 {%0, %1}, [%16];\n\t@q ld.global.nc.v2.f64 {%2, %3}, [%16+16];\n\t"
-        "@q ld.global.nc.v2.f64 {%4, %5}, [%16+%18];\n\t@q ld.global.nc.v2.f64 {%6, %7}, [%16+%18+16];\n\t"
-        "@q ld.global.nc.v2.f64 {%8, %9}, [%16+%19];\n\t@q ld.global.nc.v2.f64 {%10, %11}, [%16+%19+16];\n\t"
-        "@q ld.global.nc.v2.f64 {%12, %13}, [%16+%20];\n\t@q ld.global.nc.v2.f64 {%14, %15}, [%16+%20+16];\n\t}"
+        "@q ld.global.nc.v2.f64 {%0, %1}, [%16];\n\t@q ld.global.nc.v2.f64 {%2, %3}, [%16+128];\n\t"
+        "@q ld.global.nc.v2.f64 {%4, %5}, [%16+%18];\n\t@q ld.global.nc.v2.f64 {%6, %7}, [%16+%18+128];\n\t"
+        "@q ld.global.nc.v2.f64 {%8, %9}, [%16+%19];\n\t@q ld.global.nc.v2.f64 {%10, %11}, [%16+%19+128];\n\t"
+        "@q ld.global.nc.v2.f64 {%12, %13}, [%16+%20];\n\t@q ld.global.nc.v2.f64 {%14, %15}, [%16+%20+128];\n\t}"
         : "+d"(r[0][0]), "+d"(r[0][1]), "+d"(r[0][2]), "+d"(r[0][3]), "+d"(r[1][0]), "+d"(r[1][1]), "+d"(r[1][2]), "+d"(r[1][3]),
           "+d"(r[2][0]), "+d"(r[2][1]), "+d"(r[2][2]), "+d"(r[2][3]), "+d"(r[3][0]), "+d"(r[3][1]), "+d"(r[3][2]), "+d"(r[3][3])
         : "l"(p), "r"((int)pred), "n"(kC10 * 8), "n"(kC01 * 8), "n"(kC11 * 8));
@@ -121,7 +123,10 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 // NV     register-cached varying bilinear gases (1 or 3); the call's nvar may be smaller
 // LUT32  cache the look-up-table rows as fp32 (exact: the files are f4) and widen them in the FMA chain
 // R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH>
+// L      positions (layers) per hand-off: record slots and staging tiles change hands in groups of L, so that the
+//        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
+// ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -136,14 +141,15 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     constexpr int NPW = kQNH - 1;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *stage = smem_raw;                                           // [NBUF][NOUT][TILEB]  (1024-byte aligned)
-    unsigned char *zero_tile = stage + (size_t)NBUF * NOUT * TILEB;            // SW: source of the g = 0 plane
+    static_assert(R % L == 0 && L <= kQNI, "record ring: whole groups; every position of a group comes from a different index warp");
+    unsigned char *stage = smem_raw;                                           // [NBUF][L][NOUT][TILEB]  (1024-byte aligned)
+    unsigned char *zero_tile = stage + (size_t)NBUF * L * NOUT * TILEB;        // SW: source of the g = 0 plane
     RecT *recs = reinterpret_cast<RecT *>(zero_tile + (SW ? BOXB : 0));        // [R]
     unsigned long long *tile_full = reinterpret_cast<unsigned long long *>(recs + R);
     unsigned long long *tile_empty = tile_full + NBUF;
     unsigned long long *rec_full = tile_empty + NBUF;
-    unsigned long long *rec_empty = rec_full + R;
-    float2 *spl2 = reinterpret_cast<float2 *>(rec_empty + R);                  // LW: Planck LUT of this g-group, [g][row] (row, row+1)
+    unsigned long long *rec_empty = rec_full + R / L;
+    float2 *spl2 = reinterpret_cast<float2 *>(rec_empty + R / L);                  // LW: Planck LUT of this g-group, [g][row] (row, row+1)
 
     // logical warp order [compute | index | store | helpers]; hardware warp ids run the other way round because the
     // issue arbiter prefers the highest warp id: the compute warps get priority over the throughput-oriented helpers
@@ -153,13 +159,14 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     const int ntile_all = (ncol + kQCols - 1) / kQCols;
     const int nslot = (ntile_all - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this block: b, b + grid, ...
     const int S = nslot * nlay;                                                             // stream positions of this block
+    const int Spad = (S + L - 1) / L * L;                                                   // ... in whole hand-off groups
     const size_t pitch = (size_t)ncol, plane = (size_t)ncol * nlay;
     const bool has_lut = cg.lut >= 0, has_mix = cg.nmix > 0;
     const int nvar = cg.nvar;
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tile_full[b], kQNCW); mbar_init(&tile_empty[b], 1); }
-        for (int q = 0; q < R; ++q) { mbar_init(&rec_full[q], 1); mbar_init(&rec_empty[q], kQNCW); }
+        for (int q = 0; q < R / L; ++q) { mbar_init(&rec_full[q], L); mbar_init(&rec_empty[q], kQNCW); }
     }
     if (!SW) {   // each entry holds the row AND its upper neighbour: one 8-byte LDS fetches both interpolation operands
         const int np_ = m.nplanck;
@@ -180,31 +187,36 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     if (warp >= kQNCW + kQNI) {
         reg_dec<RH>();
         const int hw = warp - (kQNCW + kQNI);
+        if (ECCKD_DBG(128) && hw == 0) return;   // experiment: Planck warps only
         if (hw == 0) {
             // ---- store warp: staging tiles -> cp.async.bulk.tensor stores ----
             if (lane == 0) {
                 int b = 0, par = 0, ts = 0, j = 0;
-                for (int s = 0; s < S; ++s) {
-                    const int col0 = ((int)blockIdx.x + ts * (int)gridDim.x) * kQCols;
+                for (int s0 = 0; s0 < S; s0 += L) {
                     mbar_wait_relaxed(&tile_full[b], par, kStoreNap);
-                    const unsigned char *sb = stage + (size_t)b * NOUT * TILEB;
 #pragma unroll
-                    for (int o = 0; o < NOUT; ++o)
-                        if (a.out[o]) {
+                    for (int l = 0; l < L; ++l) {
+                        if (s0 + l >= S) break;                          // padding positions of the last group
+                        const int col0 = ((int)blockIdx.x + ts * (int)gridDim.x) * kQCols;
+                        const unsigned char *sb = stage + (size_t)(b * L + l) * NOUT * TILEB;
+#pragma unroll
+                        for (int o = 0; o < NOUT; ++o)
+                            if (a.out[o] && !ECCKD_DBG(1)) {
+#pragma unroll
+                                for (int h = 0; h < NBOX; ++h)
+                                    if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[o], sb + o * TILEB + h * BOXB, col0 + 16 * h, j, g0);
+                            }
+                        if (SW && ZERO_BY_TMA && a.out[2] && !ECCKD_DBG(1)) {
 #pragma unroll
                             for (int h = 0; h < NBOX; ++h)
-                                if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[o], sb + o * TILEB + h * BOXB, col0 + 16 * h, j, g0);
+                                if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[2], zero_tile, col0 + 16 * h, j, g0);   // g = 0  :460
                         }
-                    if (SW && a.out[2]) {
-#pragma unroll
-                        for (int h = 0; h < NBOX; ++h)
-                            if (h == 0 || col0 + 16 < ncol) tma_store_3d(&maps.m[2], zero_tile, col0 + 16 * h, j, g0);   // g = 0  :460
+                        if (++j == nlay) { j = 0; ++ts; }
                     }
                     tma_commit();
-                    tma_wait_read<0>();                  // the tile has been read out of shared memory: hand it back
+                    tma_wait_read<0>();                  // the tiles have been read out of shared memory: hand them back
                     mbar_arrive(&tile_empty[b]);
                     if (++b == NBUF) { b = 0; par ^= 1; }
-                    if (++j == nlay) { j = 0; ++ts; }
                 }
                 tma_wait_all<0>();
             }
@@ -213,12 +225,19 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         const int pw = hw - 1;
         const int ng = min(kGP, ngpt - g0);
         if (SW) {
-            // ---- toa_src(:, g) = solar_irradiance(g)   :468-472 (lanes = columns) ----
-            if (a.out2d) {
-                for (int ts = pw; ts < nslot; ts += NPW) {
-                    const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
-                    if (cc < ncol)
-                        for (int gq = 0; gq < ng; ++gq) a.out2d[cc + (long long)ncol * (g0 + gq)] = (Real)m.solar[g0 + gq];
+            // ---- source warps (SW): lanes = columns.  toa_src(:, g) = solar_irradiance(g) :468-472 and the g = 0
+            //      plane :460, written with plain 256-byte row stores: it does not have to pass through the TMA unit ----
+            for (int ts = 0; ts < nslot; ++ts) {
+                const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+                if (cc >= ncol) continue;
+                if (a.out2d && ts % NPW == pw)
+                    for (int gq = 0; gq < ng; ++gq) a.out2d[cc + (long long)ncol * (g0 + gq)] = (Real)m.solar[g0 + gq];
+                if (a.out[2] && !ZERO_BY_TMA) {
+                    for (int j = pw; j < nlay; j += NPW) {
+                        char *pz = reinterpret_cast<char *>(a.out[2] + ((size_t)cc + pitch * (size_t)j + plane * (size_t)g0));
+#pragma unroll 4
+                        for (int gq = 0; gq < ng; ++gq, pz += plane * sizeof(Real)) store_cs(reinterpret_cast<Real *>(pz), (Real)0);
+                    }
                 }
             }
             return;
@@ -261,28 +280,48 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
                 const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
                 char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
-                int so = 0;
+                // g-points in batches of GB: all table reads of a batch are issued before its arithmetic and its
+                // stores, so that a batch is GB independent chains instead of one serial LDS -> F2F -> FMA -> STG chain
+                constexpr int GB = 4;
                 if (has_lev) {
                     it = planck_index(m, tv, a0, a1);
                     const float2 *tv_p = spl2 + (max(it, 1) - 1);
                     const Real v0 = (Real)__ddiv_rn(a0, m.pi), v1 = (Real)__ddiv_rn(a1, m.pi);
                     char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
                     char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
-#pragma unroll 4
-                    for (int gq = 0; gq < ng; ++gq, so += S_, p_lay += plane_b, p_dec += plane_b, p_inc += plane_b) {
-                        const float2 pl = tl_p[so], pv = tv_p[so];
-                        const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
-                        const Real vv = fma_(v1, (Real)pv.y, mul_(v0, (Real)pv.x));      // B(tlev(:,j))
-                        stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay);
-                        stcs_if(reinterpret_cast<Real *>(p_dec), vv, ok_lay);            // lev_source_dec(:,j)   :424
-                        stcs_if(reinterpret_cast<Real *>(p_inc), vv, ok_inc);            // lev_source_inc(:,j-1) :423
+                    for (int gq = 0; gq < ng; gq += GB) {
+                        float2 pl[GB], pv[GB];
+#pragma unroll
+                        for (int k = 0; k < GB; ++k) {
+                            const int so = min(gq + k, ng - 1) * S_;
+                            pl[k] = tl_p[so]; pv[k] = tv_p[so];
+                        }
+                        Real vl[GB], vv[GB];
+#pragma unroll
+                        for (int k = 0; k < GB; ++k) {
+                            vl[k] = fma_(l1, (Real)pl[k].y, mul_(l0, (Real)pl[k].x));
+                            vv[k] = fma_(v1, (Real)pv[k].y, mul_(v0, (Real)pv[k].x));      // B(tlev(:,j))
+                        }
+#pragma unroll
+                        for (int k = 0; k < GB; ++k) {
+                            const bool gk = gq + k < ng;
+                            stcs_if(reinterpret_cast<Real *>(p_lay), vl[k], ok_lay && gk);
+                            stcs_if(reinterpret_cast<Real *>(p_dec), vv[k], ok_lay && gk);            // lev_source_dec(:,j)   :424
+                            stcs_if(reinterpret_cast<Real *>(p_inc), vv[k], ok_inc && gk);            // lev_source_inc(:,j-1) :423
+                            p_lay += plane_b; p_dec += plane_b; p_inc += plane_b;
+                        }
                     }
                 } else {
-#pragma unroll 4
-                    for (int gq = 0; gq < ng; ++gq, so += S_, p_lay += plane_b) {
-                        const float2 pl = tl_p[so];
-                        const Real vl = fma_(l1, (Real)pl.y, mul_(l0, (Real)pl.x));
-                        stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay);
+                    for (int gq = 0; gq < ng; gq += GB) {
+                        float2 pl[GB];
+#pragma unroll
+                        for (int k = 0; k < GB; ++k) pl[k] = tl_p[min(gq + k, ng - 1) * S_];
+#pragma unroll
+                        for (int k = 0; k < GB; ++k) {
+                            const Real vl = fma_(l1, (Real)pl[k].y, mul_(l0, (Real)pl[k].x));
+                            stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && gq + k < ng);
+                            p_lay += plane_b;
+                        }
                     }
                 }
             }
@@ -308,19 +347,41 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // ================================ index warps =====================================
     if (warp >= kQNCW) {
         reg_dec<RI>();
+        if (ECCKD_DBG(128)) return;
         const int iw = warp - kQNCW;
         int ts = 0, j = iw;                                    // position s = ts * nlay + j
         while (j >= nlay) { j -= nlay; ++ts; }
         int slot = iw % R, n = iw / R;                          // ring slot of s and how often it has been used before
-        for (int s = iw; s < S; s += kQNI) {
-            const long long col = min((long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane, (long long)ncol - 1);
+        // The inputs of a position stream in from DRAM (latency of microseconds under the kernel's write load): they are
+        // fetched one position ahead of the arithmetic, like the Planck warps do.
+        struct In { double pu, pl, tl, vl, vv[NV]; };
+        auto fetch = [&](int ts_, int j_, In &in) {
+            const long long col = min((long long)((int)blockIdx.x + ts_ * (int)gridDim.x) * kQCols + lane, (long long)ncol - 1);
             // (tail tiles recompute the last column; never stored)
+            in.pu = (double)a.plev[col + (long long)ncol * j_];
+            in.pl = (double)a.plev[col + (long long)ncol * (j_ + 1)];
+            in.tl = (double)a.tlay[col + (long long)ncol * j_];
+            in.vl = has_lut ? load_vmr<Real>(cg.g[cg.lut], col, j_) : 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) in.vv[v] = v < nvar ? load_vmr<Real>(cg.g[cg.var_gas[v]], col, j_) : 0.0;
+        };
+        In nxt;
+        if (iw < S) fetch(ts, j, nxt);
+        for (int s = iw; s < Spad; s += kQNI) {
+            const In in = nxt;
+            {
+                int j2 = j + kQNI, ts2 = ts;
+                while (j2 >= nlay) { j2 -= nlay; ++ts2; }
+                if (s + kQNI < S) fetch(ts2, j2, nxt);
+            }
             P c01, c23, lutw, wv[(NV + 2) / 2], aux;
             int2 key;
-            {
-                const double pu = (double)a.plev[col + (long long)ncol * j], pl = (double)a.plev[col + (long long)ncol * (j + 1)];
-                const double tl = (double)a.tlay[col + (long long)ncol * j];
-                const CellIndex ci = cell_index(m, pu, pl, tl);
+            if ((ECCKD_DBG(2) && s >= R) || s >= S) {   // (s >= S: padding position of the last hand-off group, never stored)
+                c01 = c23 = lutw = aux = make_pair_<P>(0.25, 0.25); key = make_int2(0, 0);
+#pragma unroll
+                for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = c01;
+            } else {
+                const CellIndex ci = cell_index(m, in.pu, in.pl, in.tl);
                 const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
                 c01 = make_pair_<P>(__dmul_rn(tw0, pw0), __dmul_rn(tw0, ci.pw1));
                 c23 = make_pair_<P>(__dmul_rn(ci.tw1, pw0), __dmul_rn(ci.tw1, ci.pw1));
@@ -335,8 +396,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 for (int v = 0; v < NV; ++v) {
                     double wd = 0.0;
                     if (v < nvar) {
-                        const GasRef &gr = cg.g[cg.var_gas[v]];
-                        wd = gas_weight(gr, ci.sw, load_vmr<Real>(gr, col, j));
+                        wd = gas_weight(cg.g[cg.var_gas[v]], ci.sw, in.vv[v]);
                         if (wd < 0.0) wd = 0.0;
                     }
                     W[v + 1] = wd;
@@ -349,22 +409,21 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 lutw = make_pair_<P>(0.0, 0.0);
                 if (has_lut) {
                     const GasRef &gr = cg.g[cg.lut];
-                    const double vmr = load_vmr<Real>(gr, col, j);
                     double v1;
-                    const int iv = vmr_index(gr, vmr, v1) - 1;
+                    const int iv = vmr_index(gr, in.vl, v1) - 1;
                     key.y = ((iv * kNPP + ip) * kNTP + it) * kGP;
-                    double wd = gas_weight(gr, ci.sw, vmr);
+                    double wd = gas_weight(gr, ci.sw, in.vl);
                     if (wd < 0.0) wd = 0.0;
                     lutw = make_pair_<P>(wd, v1);
                 }
             }
-            if (n >= 1) mbar_wait_relaxed(&rec_empty[slot], (n - 1) & 1, kIndexNap);
+            if (n >= 1) mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap);
             RecT &rc = recs[slot];
             rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane] = key;
 #pragma unroll
             for (int v = 0; v < (NV + 2) / 2; ++v) rc.w[v][lane] = wv[v];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&rec_full[slot]);
+            if (lane == 0) mbar_arrive(&rec_full[slot / L]);
             j += kQNI; while (j >= nlay) { j -= nlay; ++ts; }
             slot += kQNI; while (slot >= R) { slot -= R; ++n; }
         }
@@ -373,14 +432,17 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     // ================================ compute warps ===================================
     reg_inc<RC>();
+    if (ECCKD_DBG(128)) return;
     const int cw = lane >> 3, q = lane & 7;            // column of the warp's quad, lane of the column
     const int ct = 4 * warp + cw;                      // column of the tile
     const int ngroups = gridDim.y;
-    // table pointers of this lane: 4 consecutive (permuted) positions = g-points q, q+8, q+16, q+24
+    // table pointers of this lane (rows are stored permuted, see walk_pos32 / walk_pos64): 4-byte rows hold the lane's
+    // g-points q, q+8, q+16, q+24 as one 16-byte vector at 4q; 8-byte rows as two vectors at 2q and 16 + 2q
+    constexpr int LQ = sizeof(LutT) == 8 ? 2 : 4, MQ = sizeof(Real) == 8 ? 2 : 4;
     const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + 4 * q;
     const LutT *wlut = (LUT32 ? reinterpret_cast<const LutT *>(m.wlut32) : reinterpret_cast<const LutT *>(TableOf<Real>::wlut(m))) +
-                       (size_t)grp * m.nv_lut * kSlab + 4 * q;
-    const Real *wmix = mixtab + (size_t)grp * kSlab + 4 * q;     // negative-sign copy at + ngroups*kSlab
+                       (size_t)grp * m.nv_lut * kSlab + LQ * q;
+    const Real *wmix = mixtab + (size_t)grp * kSlab + MQ * q;    // negative-sign copy at + ngroups*kSlab
     const float *wvar[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) wvar[v] = wbil + (v < nvar ? cg.var_off[v] : 0);
@@ -403,17 +465,24 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     // (re)load the register cache for corner offsets (pkoff, hkoff); every load is predicated on "this column's key
     // moved", so the four columns of the warp refill independently without divergence
-    auto refill = [&](int pkoff, int hkoff) {
-        const bool pb = pkoff != cur_pk, pl = has_lut && hkoff != cur_hk;
+    auto refill_lut = [&](int hkoff) {
+        const bool pl = has_lut && hkoff != cur_hk;
+        if (!ECCKD_DBG(8)) {
+            ld_rows_if(kh[0], wlut + hkoff, pl);
+            ld_rows_if(kh[1], wlut + hkoff + kSlab, pl);
+        }
+        cur_hk = hkoff;
+    };
+    auto refill_bil = [&](int pkoff) {
+        const bool pb = pkoff != cur_pk;
         if (!ECCKD_DBG(8)) {
             ld_rows_if(km, wmix + pkoff, pb && has_mix);
 #pragma unroll
             for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, pb && v < nvar);
-            ld_rows_if(kh[0], wlut + hkoff, pl);
-            ld_rows_if(kh[1], wlut + hkoff + kSlab, pl);
         }
-        cur_pk = pkoff; cur_hk = hkoff;
+        cur_pk = pkoff;
     };
+    auto refill = [&](int pkoff, int hkoff) { refill_bil(pkoff); refill_lut(hkoff); };
 
     // staging address of this lane's first value (g-point q): row = g, 16-byte chunks XOR-swizzled with (row & 7) = q
     // exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out; value i (g-point q + 8 i) is 8 rows = 1024 bytes further
@@ -441,52 +510,65 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     for (int v = 0; v < NV; ++v) keep(wvar[v]);
 
     if (S > 0) {
+        // The record of a position is read into registers one position ahead, BEFORE the cache refill is issued: the
+        // LSU queue is in order, so a record load behind 28 refill loads would wait for all of them.
+        struct Cur { P c01, c23, lw, wv[(NV + 2) / 2]; Real swt; int2 key; } cur;
+        auto load_rec = [&](int slot_) {
+            const unsigned ra = rec_a + slot_ * RB;
+            cur.key = lds_int2(key_a + slot_ * RB);
+            cur.c01 = lds_pair<P>(ra + O_C01); cur.c23 = lds_pair<P>(ra + O_C23); cur.lw = lds_pair<P>(ra + O_LUT);
+#pragma unroll
+            for (int v = 0; v < (NV + 2) / 2; ++v) cur.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
+            cur.swt = SW ? lds_pair<P>(ra + O_AUX).x : (Real)0;
+        };
         mbar_wait_a(a_rfull, 0);
-        int2 key = lds_int2(key_a);
-        refill(key.x & 0xffff, key.y);
+        load_rec(0);
+        refill(cur.key.x & 0xffff, cur.key.y);
         int slot = 0, rpar = 0, b = 0, tpar = 1;       // tpar: parity to wait for on tile_empty (the phase before the
                                                        // initial one counts as complete, so the first pass never blocks)
-        for (int s = 0; s < S; ++s) {
-            const unsigned ra = rec_a + slot * RB;
-            const P c01 = lds_pair<P>(ra + O_C01), c23 = lds_pair<P>(ra + O_C23), lw = lds_pair<P>(ra + O_LUT);
-            P wv[(NV + 2) / 2];
-#pragma unroll
-            for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
-            const Real c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
-            const Real omv = add_((Real)1, -lw.y);
+        int ls = 0;                                    // position inside the hand-off group
+        for (int s = 0; s < Spad; ++s) {
+            const Real c0 = cur.c01.x, c1 = cur.c01.y, c2 = cur.c23.x, c3 = cur.c23.y;
+            const Real omv = add_((Real)1, -cur.lw.y);
             Real tau[4];
+            const int nslot_r = slot + 1 == R ? 0 : slot + 1;
+            if (ECCKD_DBG(4)) { tau[0] = c0; tau[1] = c1; tau[2] = c2; tau[3] = c3; }
+            else
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const Real b0 = bil4(c0, c1, c2, c3, kh[0][0][i], kh[0][1][i], kh[0][2][i], kh[0][3][i]);
                 const Real b1 = bil4(c0, c1, c2, c3, kh[1][0][i], kh[1][1][i], kh[1][2][i], kh[1][3][i]);
                 const Real bm = bil4(c0, c1, c2, c3, km[0][i], km[1][i], km[2][i], km[3][i]);
                 // (1-v1)*b0 + v1*b1, not b0 + v1*(b1-b0): that cancels when b1 << b0
-                Real t = mul_(lw.x, fma_(lw.y, b1, mul_(omv, b0)));
-                t = fma_(wv[0].x, bm, t);
+                Real t = mul_(cur.lw.x, fma_(cur.lw.y, b1, mul_(omv, b0)));
+                t = fma_(cur.wv[0].x, bm, t);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const Real bv = bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
-                    const Real wgt = ((v + 1) & 1) ? wv[(v + 1) >> 1].y : wv[(v + 1) >> 1].x;
+                    const Real wgt = ((v + 1) & 1) ? cur.wv[(v + 1) >> 1].y : cur.wv[(v + 1) >> 1].x;
                     t = fma_(wgt, bv, t);
                 }
                 tau[i] = t;
             }
-            if (key.x & kNegFlag) {   // upside-down layer: the negative-factor gases give positive optical depth
-                const Real *k = wmix + (size_t)ngroups * kSlab + (key.x & 0xffff);
-                const Real swt = lds_pair<P>(ra + O_AUX).x;
+            if (cur.key.x & kNegFlag) {   // upside-down layer: the negative-factor gases give positive optical depth
+                const Real *k = wmix + (size_t)ngroups * kSlab + (cur.key.x & 0xffff);
+                const Real swn = lds_pair<P>(rec_a + slot * RB + O_AUX).x;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tau[i] = fma_(swt, bil4(c0, c1, c2, c3, k[kC00 + i], k[kC10 + i], k[kC01 + i], k[kC11 + i]), tau[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const int e = sizeof(Real) == 8 ? (i >> 1) * 16 + (i & 1) : i;    // element of g-point q + 8 i in this lane's row slice
+                    tau[i] = fma_(swn, bil4(c0, c1, c2, c3, k[kC00 + e], k[kC10 + e], k[kC01 + e], k[kC11 + e]), tau[i]);
+                }
             }
-            // the cache has been read: fetch the next position's corners under the rest of this layer's work
-            const int nslot_r = slot + 1 == R ? 0 : slot + 1;
-            if (s + 1 < S) {
-                mbar_wait_a(a_rfull + nslot_r * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
-                key = lds_int2(key_a + nslot_r * RB);
-                refill(key.x & 0xffff, key.y);
+            const Real swt = cur.swt;
+            // the cache and the record have been read: fetch the next position's record, then its corners, under the
+            // rest of this layer's work
+            if (s + 1 < Spad) {
+                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
+                load_rec(nslot_r);
+                refill(cur.key.x & 0xffff, cur.key.y);
             }
             Real ssa[4];
             if (SW) {
-                const Real swt = lds_pair<P>(ra + O_AUX).x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const Real ray = mul_(swt, sigma[i]);             // :313-316 (moles_per_layer == simple_weight, same product)
@@ -494,20 +576,25 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     ssa[i] = div_fast(ray, tau[i]);                   // :459
                 }
             }
-            mbar_wait_a(a_tempty + b * 8, tpar);
-            const unsigned sa = stage_a + b * (NOUT * TILEB);
+            if (ls == 0) mbar_wait_a(a_tempty + b * 8, tpar);
+            const unsigned sa = stage_a + (b * L + ls) * (NOUT * TILEB);
+            if (!ECCKD_DBG(16)) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sts_<Real>(sa + i * 1024, tau[i]);
-                if (SW) sts_<Real>(sa + TILEB + i * 1024, ssa[i]);
+                for (int i = 0; i < 4; ++i) {
+                    sts_<Real>(sa + i * 1024, tau[i]);
+                    if (SW) sts_<Real>(sa + TILEB + i * 1024, ssa[i]);
+                }
             }
-            fence_proxy_async_smem();          // generic-proxy writes -> visible to the async (TMA) proxy
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_a(a_tfull + b * 8);
-                mbar_arrive_a(a_rempty + slot * 8);
+            if (++ls == L) {
+                ls = 0;
+                if (!ECCKD_DBG(16)) fence_proxy_async_smem();      // generic-proxy writes -> visible to the async (TMA) proxy
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_a(a_tfull + b * 8);
+                    mbar_arrive_a(a_rempty + (slot / L) * 8);
+                }
+                if (++b == NBUF) { b = 0; tpar ^= 1; }
             }
-            if (++b == NBUF) { b = 0; tpar ^= 1; }
             slot = nslot_r;
             if (slot == 0) rpar ^= 1;
         }
@@ -539,7 +626,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -547,9 +634,9 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
     TmaMaps maps{};
     for (int o = 0; o < (SW ? 3 : 1); ++o)
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)NBUF * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV>) * R +
-                        (2 * NBUF + 2 * R) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH>;
+    const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV>) * R +
+                        (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
@@ -570,16 +657,42 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
-        if (v == 1) return launch_quad_t<Real, SW, 1, false, 8, 4>(m, cg, a, mix, sms, s);
-        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 8>(m, cg, a, mix, sms, s);
-        if (v == 3) return launch_quad_t<Real, SW, 1, false, 32, 6>(m, cg, a, mix, sms, s);
-        if (v == 4) return launch_quad_t<Real, SW, 1, true, 16, 6>(m, cg, a, mix, sms, s);
-        if (v == 5) return launch_quad_t<Real, SW, 1, true, 8, 4>(m, cg, a, mix, sms, s);
-        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 80>(m, cg, a, mix, sms, s);
+        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA
+        if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 80>(m, cg, a, mix, sms, s);
+        if (v == 3) return launch_quad_t<Real, SW, 1, true, 16, 6, 184, 64, 64>(m, cg, a, mix, sms, s);
+        if (v == 4) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 96, 112>(m, cg, a, mix, sms, s);
+        if (v == 5) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 112, 96>(m, cg, a, mix, sms, s);
+        if (v == 6) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128>(m, cg, a, mix, sms, s);
+        if (v == 7) return launch_quad_t<Real, SW, 1, true, 8, 4, 152, 96, 112>(m, cg, a, mix, sms, s);
+        if (v == 8) return launch_quad_t<Real, SW, 1, true, 32, 8, 152, 96, 112>(m, cg, a, mix, sms, s);
+        if (v == 9) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88>(m, cg, a, mix, sms, s);
+        if (v == 21) return launch_quad_t<Real, SW, 1, true, 16, 3, 152, 80, 128, false, 2>(m, cg, a, mix, sms, s);
+        if (v == 22) return launch_quad_t<Real, SW, 1, true, 16, 2, 152, 80, 128, false, 4>(m, cg, a, mix, sms, s);
+        if (v == 23) return launch_quad_t<Real, SW, 1, false, 16, 3, 184, 64, 64, true, 2>(m, cg, a, mix, sms, s);
+        if (v == 24) return launch_quad_t<Real, SW, 1, false, 16, 2, 184, 64, 64, true, 4>(m, cg, a, mix, sms, s);
+        if (v == 25) return launch_quad_t<Real, SW, 1, false, 16, 3, 168, 80, 80, false, 2>(m, cg, a, mix, sms, s);
+        if (v == 26) return launch_quad_t<Real, SW, 1, false, 16, 2, 168, 80, 80, false, 4>(m, cg, a, mix, sms, s);
+        if (v == 27) return launch_quad_t<Real, SW, 1, true, 32, 4, 152, 80, 128, false, 4>(m, cg, a, mix, sms, s);
+        if (v == 28) return launch_quad_t<Real, SW, 1, false, 32, 4, 184, 64, 64, true, 4>(m, cg, a, mix, sms, s);
+        if (v == 11) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 96, 32, true>(m, cg, a, mix, sms, s);
+        if (v == 12) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 128, 80, true>(m, cg, a, mix, sms, s);
+        if (v == 13) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 88, 40, true>(m, cg, a, mix, sms, s);
+        if (v == 10) return launch_quad_t<Real, SW, 1, true, 16, 6, 160, 104, 88>(m, cg, a, mix, sms, s);
     }
 #endif
-    if (cg.nvar <= 1) return launch_quad_t<Real, SW, 1, false, 16, 6>(m, cg, a, mix, sms, s);
-    return launch_quad_t<Real, SW, kQuadMaxVar, false, 16, 6>(m, cg, a, mix, sms, s);
+    // Production instantiations, as measured on B200 (tools/exp_quad.sh):
+    //   LW  look-up-table rows cached as fp32 (half the refill bytes and 32 registers less per compute thread); the
+    //       registers go to the Planck warps (128: batches of four g-points in flight) and the index warps (80)
+    //   SW  no Planck role: compute warps keep the LUT at full width (no conversions next to the ssa division), the
+    //       g = 0 plane leaves through the TMA unit
+    //                                          NV  LUT32   R NBUF   RC   RI   RH  ZERO_BY_TMA
+    if (cg.nvar <= 1) {
+        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false>(m, cg, a, mix, sms, s);
+    }
+    if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+    else return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 176, 72, 88, false>(m, cg, a, mix, sms, s);
 }
 
 #define ECCKD_QUAD_INST(Real)                                                                                                   \
