@@ -187,7 +187,13 @@ int ecckd_gas_optics_sw_f32(ecckd_model *model, int dev_index, int ncol, int nla
  * Synchronous.  Columns are split into contiguous shards over the model's
  * devices (no collective: columns are independent) and, within a device, into
  * blocks of `block_cols` columns (0 = library default) that are pipelined
- * H2D -> kernel -> D2H through pinned staging buffers on that device's stream.
+ * H2D -> kernel -> D2H over three stream slots per device.  The copies run
+ * straight between the caller's arrays and device buffers: caller arrays of
+ * 8 MiB or more (ECCKD_PIN_MIN_BYTES) are page-locked in place for the duration
+ * of the call (cudaHostRegister) so that the slots really overlap; arrays the
+ * caller has pinned already are used as they are, smaller pageable ones go
+ * through the driver's staged copies.  Device block buffers have their own
+ * (even) column pitch, so any `ncol` takes the TMA-store kernel.
  * Same semantics and error behaviour as the device entry points. */
 int ecckd_gas_optics_lw_host_f64(ecckd_model *model, int ncol, int nlay,
                                  const double *plev, const double *tlay, const double *tlev, const double *tsfc,

@@ -243,6 +243,7 @@ HostModel load_and_init(const std::string &filename)
 
     const std::vector<double> &w1 = var(nc, "wavenumber1_band").data, &w2 = var(nc, "wavenumber2_band").data;
     m.nband = (int)w1.size();                                                             // :55-58
+    if (m.nband < 1 || w2.size() != w1.size()) throw std::runtime_error("load_and_init_ecckd: file has no bands");
     m.band_lims_wvn.resize(2 * (size_t)m.nband);
     for (int b = 0; b < m.nband; ++b) { m.band_lims_wvn[2 * b] = w1[b]; m.band_lims_wvn[2 * b + 1] = w2[b]; }
     const std::vector<double> &bn = var(nc, "band_number").data;                          // :60-63

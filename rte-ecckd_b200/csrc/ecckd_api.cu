@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ck_loader.h"
 #include "ecckd_b200.h"
 #include "ecckd_device.cuh"
@@ -37,6 +39,12 @@ struct DevState {
     DevModel dm{};
     std::vector<void *> allocs;
     Slot slots[kSlots];
+};
+
+// NVTX range for the profilers' timelines (H2D / table mix + walk / D2H); a no-op without an attached tool
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 void set_err(char *err, const std::string &msg)
@@ -213,6 +221,7 @@ int run_device(ecckd_model *M, int dev_index, bool sw, int ncol, int nlay, const
         } else if (kernel == ECCKD_KERNEL_GENERIC) use_walk = false;
         else { set_err(err, "ecckd: unknown kernel selector"); return ECCKD_ERR_ARG; }
         cudaError_t e;
+        NvtxRange nvtx(use_walk ? (which == 1 ? "ecckd: mix + quad kernel" : "ecckd: mix + column-walk kernel") : "ecckd: generic kernel");
         if (use_walk) {
             // stream-ordered scratch for the per-call mixed table: safe for concurrent calls on other streams
             void *scratch = nullptr;
@@ -252,6 +261,14 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
     if (err) err[0] = '\0';
     if (!M) { set_err(err, "ecckd: NULL model"); return ECCKD_ERR_ARG; }
     if (ncol < 0 || nlay < 0) { set_err(err, "ecckd: negative extent"); return ECCKD_ERR_ARG; }
+    if (ngas < 0 || ngas > ECCKD_MAX_GASES) {
+        // more names than the model can hold: unknown ones would be skipped anyway, but the view table is bounded
+        set_err(err, "ecckd: the concentration list of the host path holds 0..16 gases");
+        return ECCKD_ERR_ARG;
+    }
+    if (ngas > 0 && (!names || !vmr)) { set_err(err, "ecckd: bad gas list"); return ECCKD_ERR_ARG; }
+    for (int j = 0; j < ngas; ++j)
+        if (!names[j]) { set_err(err, "ecckd: NULL gas name"); return ECCKD_ERR_ARG; }
     const int ndev = (int)M->devs.size();
     const int ngpt = M->ngpt;
     const bool lev_missing = !sw && !tlev;
@@ -267,29 +284,28 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
         if (block_cols <= 0) block_cols = 8192;
         const long long per_dev = ((long long)ncol + ndev - 1) / ndev;
         const int B = (int)std::min<long long>(block_cols, per_dev);
+        // device block buffers get a column pitch that is a multiple of 4 elements (16 bytes in fp32): every block is
+        // then eligible for the TMA-store (quad) kernel whatever the caller's ncol; padding columns are zero-filled
+        // once, computed and never copied back
+        const int Bp = (B + 3) & ~3;
         // slot layout (same for every slot)
         Carve probe{nullptr};
         auto carve = [&](Carve &c, Real *&d_plev, Real *&d_tlay, Real *&d_tlev, Real *&d_tsfc, Real **d_vmr, Real **d_out, Real *&d_2d) {
-            d_plev = c.take<Real>((size_t)B * (nlay + 1));
-            d_tlay = c.take<Real>((size_t)B * nlay);
-            d_tlev = c.take<Real>((size_t)B * (nlay + 1));
-            d_tsfc = c.take<Real>((size_t)B);
+            d_plev = c.take<Real>((size_t)Bp * (nlay + 1));
+            d_tlay = c.take<Real>((size_t)Bp * nlay);
+            d_tlev = c.take<Real>((size_t)Bp * (nlay + 1));
+            d_tsfc = c.take<Real>((size_t)Bp);
             for (int j = 0; j < ngas; ++j) {
                 const ecckd_vmr_view &v = vmr[j];
                 size_t n = !v.ptr ? 0 : (v.col_stride == 0 ? (v.lay_stride == 0 ? 1 : (size_t)nlay)
-                                                            : (v.lay_stride == 0 ? (size_t)B : (size_t)B * nlay));
+                                                            : (v.lay_stride == 0 ? (size_t)Bp : (size_t)Bp * nlay));
                 d_vmr[j] = c.take<Real>(n);
             }
-            for (int o = 0; o < 4; ++o) d_out[o] = c.take<Real>((size_t)B * nlay * ngpt);
-            d_2d = c.take<Real>((size_t)B * ngpt);
+            for (int o = 0; o < 4; ++o) d_out[o] = c.take<Real>((size_t)Bp * nlay * ngpt);
+            d_2d = c.take<Real>((size_t)Bp * ngpt);
         };
         {
             Real *a, *b, *c2, *d2, *e2, *v2[ECCKD_MAX_GASES], *o[4];
-            if (ngas > ECCKD_MAX_GASES) {
-                // more names than the model can hold: unknown ones are skipped anyway, but keep the view table bounded
-                set_err(err, "ecckd: more than 16 gases in the concentration list (host path)");
-                return ECCKD_ERR_ARG;
-            }
             carve(probe, a, b, c2, d2, v2, o, e2);
         }
         const size_t need = probe.off + 256;
@@ -302,11 +318,37 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
                     if (s.arena) { CUDA_TRY(cudaStreamSynchronize(s.stream)); CUDA_TRY(cudaFree(s.arena)); s.arena = nullptr; s.capacity = 0; }
                     CUDA_TRY(cudaMalloc(&s.arena, need));
                     s.capacity = need;
+                    CUDA_TRY(cudaMemsetAsync(s.arena, 0, need, s.stream));
                 }
             }
         }
         const long long nblk = (per_dev + B - 1) / B;
         const size_t rs = sizeof(Real);
+        // Pageable caller arrays (what a Fortran host model passes) make every cudaMemcpy2DAsync below a synchronous,
+        // driver-staged copy: the three pipeline slots would not overlap.  Large arrays are therefore page-locked in
+        // place for the duration of the call (cudaHostRegister; arrays the caller already pinned report
+        // "already registered" and are left alone, small ones are not worth the registration cost).
+        struct Pin {
+            std::vector<void *> ptrs;
+            ~Pin() { for (void *p : ptrs) cudaHostUnregister(p); }
+            void add(const void *p, size_t bytes) {
+                static const size_t min_bytes = [] { const char *e = getenv("ECCKD_PIN_MIN_BYTES"); return e ? (size_t)atoll(e) : (size_t)8 << 20; }();
+                if (!p || bytes < min_bytes) return;
+                if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) ptrs.push_back(const_cast<void *>(p));
+                else (void)cudaGetLastError();   // already pinned by the caller, or not registrable: copies still work
+            }
+        } pin;
+        {
+            NvtxRange nvtx("ecckd: page-lock caller arrays");
+            const size_t n3 = (size_t)ncol * nlay * ngpt * rs;
+            pin.add(o0, n3);
+            if (!(sw && not_2str)) { pin.add(o1, n3); pin.add(o2, n3); }
+            if (!sw && !lev_missing) pin.add(o3, n3);
+            pin.add(plev, (size_t)ncol * (nlay + 1) * rs); pin.add(tlay, (size_t)ncol * nlay * rs);
+            pin.add(tlev, (size_t)ncol * (nlay + 1) * rs);
+            for (int j = 0; j < ngas; ++j)
+                if (vmr[j].ptr && vmr[j].col_stride == 1 && vmr[j].lay_stride != 0) pin.add(vmr[j].ptr, (size_t)vmr[j].lay_stride * nlay * rs);
+        }
         for (long long blk = 0; blk < nblk; ++blk) {
             for (int d = 0; d < ndev; ++d) {
                 const long long c_lo = std::min<long long>((long long)d * per_dev, ncol);
@@ -314,6 +356,7 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
                 const long long c0 = c_lo + blk * B;
                 if (c0 >= c_hi) continue;
                 const int nb = (int)std::min<long long>(B, c_hi - c0);
+                const int nbp = (nb + 3) & ~3;                      // device pitch of this block (<= Bp)
                 DevState &ds = *M->devs[d];
                 CUDA_TRY(cudaSetDevice(ds.device));
                 Slot &s = ds.slots[blk % kSlots];
@@ -321,9 +364,10 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
                 Real *d_plev, *d_tlay, *d_tlev, *d_tsfc, *d_vmr[ECCKD_MAX_GASES], *d_out[4], *d_2d;
                 carve(c, d_plev, d_tlay, d_tlev, d_tsfc, d_vmr, d_out, d_2d);
                 // H2D: a column block of a (ncol, n) array is n rows of nb elements with pitch ncol
-                CUDA_TRY(cudaMemcpy2DAsync(d_plev, nb * rs, plev + c0, (size_t)ncol * rs, nb * rs, nlay + 1, cudaMemcpyHostToDevice, s.stream));
-                CUDA_TRY(cudaMemcpy2DAsync(d_tlay, nb * rs, tlay + c0, (size_t)ncol * rs, nb * rs, nlay, cudaMemcpyHostToDevice, s.stream));
-                if (tlev) CUDA_TRY(cudaMemcpy2DAsync(d_tlev, nb * rs, tlev + c0, (size_t)ncol * rs, nb * rs, nlay + 1, cudaMemcpyHostToDevice, s.stream));
+                nvtxRangePushA("ecckd: H2D block");
+                CUDA_TRY(cudaMemcpy2DAsync(d_plev, nbp * rs, plev + c0, (size_t)ncol * rs, nb * rs, nlay + 1, cudaMemcpyHostToDevice, s.stream));
+                CUDA_TRY(cudaMemcpy2DAsync(d_tlay, nbp * rs, tlay + c0, (size_t)ncol * rs, nb * rs, nlay, cudaMemcpyHostToDevice, s.stream));
+                if (tlev) CUDA_TRY(cudaMemcpy2DAsync(d_tlev, nbp * rs, tlev + c0, (size_t)ncol * rs, nb * rs, nlay + 1, cudaMemcpyHostToDevice, s.stream));
                 if (tsfc) CUDA_TRY(cudaMemcpyAsync(d_tsfc, tsfc + c0, nb * rs, cudaMemcpyHostToDevice, s.stream));
                 ecckd_vmr_view dv[ECCKD_MAX_GASES];
                 for (int j = 0; j < ngas; ++j) {
@@ -341,17 +385,19 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
                         CUDA_TRY(cudaMemcpyAsync(d_vmr[j], hp + c0, nb * rs, cudaMemcpyHostToDevice, s.stream));
                         dv[j] = ecckd_vmr_view{d_vmr[j], 1, 0};
                     } else {
-                        CUDA_TRY(cudaMemcpy2DAsync(d_vmr[j], nb * rs, hp + c0, (size_t)v.lay_stride * rs, nb * rs, nlay, cudaMemcpyHostToDevice, s.stream));
-                        dv[j] = ecckd_vmr_view{d_vmr[j], 1, nb};
+                        CUDA_TRY(cudaMemcpy2DAsync(d_vmr[j], nbp * rs, hp + c0, (size_t)v.lay_stride * rs, nb * rs, nlay, cudaMemcpyHostToDevice, s.stream));
+                        dv[j] = ecckd_vmr_view{d_vmr[j], 1, nbp};
                     }
                 }
+                nvtxRangePop();
                 char lerr[ECCKD_ERRLEN];
-                int rc = run_device<Real>(M, d, sw, nb, nlay, d_plev, d_tlay, tlev ? d_tlev : nullptr, d_tsfc, ngas, names, dv,
+                int rc = run_device<Real>(M, d, sw, nbp, nlay, d_plev, d_tlay, tlev ? d_tlev : nullptr, d_tsfc, ngas, names, dv,
                                           d_out[0], (sw && not_2str) ? nullptr : d_out[1], (sw && not_2str) ? nullptr : d_out[2],
                                           d_out[3], d_2d, ECCKD_KERNEL_AUTO, s.stream, lerr);
                 if (rc != ECCKD_OK && rc != ECCKD_ERR_REFERENCE) { set_err(err, lerr); return rc; }
                 if (rc == ECCKD_ERR_REFERENCE) { rc_final = rc; set_err(err, lerr); }
                 // D2H: every output that the reference would have written
+                NvtxRange nvtx_d2h("ecckd: D2H block");
                 Real *host_out[4] = {o0, o1, o2, o3};
                 const int nout = sw ? 3 : 4;
                 for (int o = 0; o < nout; ++o) {
@@ -359,10 +405,10 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
                     if (sw && not_2str && o > 0) written = false;
                     if (!sw && lev_missing && o >= 2) written = false;
                     if (!written || !host_out[o]) continue;
-                    CUDA_TRY(cudaMemcpy2DAsync(host_out[o] + c0, (size_t)ncol * rs, d_out[o], nb * rs, nb * rs, (size_t)nlay * ngpt, cudaMemcpyDeviceToHost, s.stream));
+                    CUDA_TRY(cudaMemcpy2DAsync(host_out[o] + c0, (size_t)ncol * rs, d_out[o], nbp * rs, nb * rs, (size_t)nlay * ngpt, cudaMemcpyDeviceToHost, s.stream));
                 }
                 if (o2d && !(sw && not_2str))
-                    CUDA_TRY(cudaMemcpy2DAsync(o2d + c0, (size_t)ncol * rs, d_2d, nb * rs, nb * rs, ngpt, cudaMemcpyDeviceToHost, s.stream));
+                    CUDA_TRY(cudaMemcpy2DAsync(o2d + c0, (size_t)ncol * rs, d_2d, nbp * rs, nb * rs, ngpt, cudaMemcpyDeviceToHost, s.stream));
             }
         }
         for (int d = 0; d < ndev; ++d) {

@@ -217,6 +217,55 @@ class GasOpticsEcckd:
         self._keep = keep
         return self
 
+    @classmethod
+    def from_components(cls, m, devices: Optional[Sequence[int]] = None) -> "GasOpticsEcckd":
+        """ecckd_model_create from the public components of a ty_gas_optics_ecckd-like object -- what the Fortran shim
+        does with the object its loader filled (gas_optics_ecckd.f90:23-36).  `m` needs the attributes shortwave, gas
+        (names), absorption[i].{coefficient, composite_only, concentration_dependence_code, mole_fraction,
+        reference_mole_fraction}, log_pressure, temperature and planck_function / temperature_planck or
+        solar_irradiance / rayleigh_molar_scattering_coeff; arrays are C-ordered with the Fortran shape reversed
+        (coefficient[v, t, p, g] == coefficient(g, p, t, v)).  Band limits are not passed (nband = 0), like the shim."""
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        keep = []
+
+        def ptr(a):
+            a = f8(a)
+            keep.append(a)
+            return a.ctypes.data
+        ngas = len(m.gas)
+        gts = (_abi.GasTable * max(ngas, 1))()
+        ngpt = None
+        for i, (name, tab) in enumerate(zip(m.gas, m.absorption)):
+            k = f8(tab.coefficient)
+            if k.ndim == 3:
+                k = k[None]
+            ngpt = k.shape[-1]
+            gts[i].name = name.encode().ljust(_abi.NAME_LEN)[:_abi.NAME_LEN]          # blank padded, like character(len=32)
+            gts[i].composite_only = int(bool(tab.composite_only))
+            gts[i].concentration_dependence_code = int(tab.concentration_dependence_code)
+            mf = getattr(tab, "mole_fraction", None)
+            gts[i].n_mole_fraction = 0 if mf is None else int(np.asarray(mf).shape[0])
+            gts[i].mole_fraction = None if mf is None else ptr(mf)
+            gts[i].reference_mole_fraction = float(tab.reference_mole_fraction)
+            gts[i].coefficient = ptr(k)
+        t = _abi.HostTables()
+        t.shortwave = int(bool(m.shortwave))
+        temperature = f8(m.temperature)                                                # [t, p]
+        t.ngpt = int(ngpt if ngpt is not None else (m.solar_irradiance if m.shortwave else m.planck_function).shape[-1])
+        t.npress, t.ntemp = int(temperature.shape[1]), int(temperature.shape[0])
+        t.num_gases = ngas
+        t.log_pressure, t.temperature = ptr(m.log_pressure), ptr(temperature)
+        if m.shortwave:
+            t.nplanck = 0
+            t.solar_irradiance, t.rayleigh_molar_scattering_coeff = ptr(m.solar_irradiance), ptr(m.rayleigh_molar_scattering_coeff)
+        else:
+            t.nplanck = int(np.asarray(m.temperature_planck).shape[0])
+            t.temperature_planck, t.planck_function = ptr(m.temperature_planck), ptr(m.planck_function)
+        t.gas = gts
+        t.nband = 0
+        keep.append(gts)
+        return cls.from_tables(t, keep, devices)
+
     def close(self) -> None:
         if self._h:
             self._lib.ecckd_model_destroy(self._h)

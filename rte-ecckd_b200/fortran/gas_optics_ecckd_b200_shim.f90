@@ -3,20 +3,31 @@
 !! Drop-in replacement of /root/reference/src/gas_optics_ecckd.f90 for the gas-optics hot
 !! path: the module name, the public type ty_gas_optics_ecckd with its public components, the
 !! AbsorptionTable helper type, the concentration-dependence codes and every type-bound
-!! procedure keep the reference's names, argument lists and error strings, so the reference's
-!! own loader (example/rfmip-rad-irf/mo_load_coefficients.F90) and drivers compile against it
-!! unchanged.  What changes is the body of gas_optics_int / gas_optics_ext: instead of the
-!! Fortran loop nests (:64-241, :245-289, :293-319 of the reference) they hand the caller's
-!! arrays to the C ABI of libecckd_b200.so (include/ecckd_b200.h), which runs sm_100a CUDA
-!! kernels.  There is no CPU fallback: if the library or a device is missing the error string
-!! says so and the driver's stop_on_err aborts.
+!! procedure keep the reference's names, argument lists, dummy characteristics and error
+!! strings, so the reference's own loader (example/rfmip-rad-irf/mo_load_coefficients.F90) and
+!! drivers (ecckd_rfmip_lw.F90:78-120, ecckd_rfmip_sw.F90:74-118) compile and run against it
+!! UNCHANGED: load_and_init, then gas_optics, nothing in between.  What changes is the body of
+!! gas_optics_int / gas_optics_ext: instead of the Fortran loop nests (:64-241, :245-289,
+!! :293-319 of the reference) they hand the caller's arrays to the C ABI of libecckd_b200.so
+!! (include/ecckd_b200.h), which runs sm_100a CUDA kernels.  There is no CPU fallback: if the
+!! library or a device is missing the error string says so and the driver's stop_on_err aborts.
 !!
-!! The device-resident tables are packed once, on the first gas_optics call (or explicitly
-!! through finalize_load), from the components the loader filled.
+!! Device model: `this` is intent(in) in both entry points, so the opaque ecckd_model handle
+!! lives in a module-level cache keyed on a signature of the tables; it is created on the first
+!! gas_optics call of an object (tables packed once, then device-resident) and shared by objects
+!! holding the same tables.  finalize_load() does the same eagerly; release_device() frees it.
 !!
-!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler and no
-!! rte-rrtmgp.  INTEGRATION.md gives the build line; tests/ exercise the very same C entry
-!! points through ctypes with the same argument meaning.
+!! Array arguments go to bind(C) interfaces with assumed-size dummies (sequence association:
+!! contiguous actuals are passed in place, others through the compiler's copy-in/copy-out), so no
+!! c_loc is ever taken of a dummy that lacks TARGET; optional arrays (tlev; ssa/g of a
+!! one-stream props object) map to NULL through optional bind(C) dummies (TS 29113 / F2018).
+!! The generic names ecckd_lw_host / ecckd_sw_host resolve to the _f64 or _f32 entry points by
+!! the kind of wp at compile time.
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler.  INTEGRATION.md
+!! gives the build line and oracle/ref/stubs the modules it compiles against; tests/c/shim_sequence.c
+!! replays this file's call sequence (model create from host tables with nband = 0 and blank-padded
+!! names, host entry points on pageable memory, error strings) in plain C on the GPU.
 module gas_optics_ecckd
 use, intrinsic :: iso_c_binding
 use, intrinsic :: iso_fortran_env, only: error_unit
@@ -39,7 +50,7 @@ type, public :: AbsorptionTable
 end type AbsorptionTable
 
 
-!> @brief ecckd gas optics (reference :23-48) plus the opaque device handle.
+!> @brief ecckd gas optics: the reference's components (:23-36), nothing added.
 type, extends(ty_gas_optics), public :: ty_gas_optics_ecckd
   type(AbsorptionTable), dimension(16) :: absorption
   character(len=32), dimension(16) :: gas
@@ -54,7 +65,6 @@ type, extends(ty_gas_optics), public :: ty_gas_optics_ecckd
   real(kind=wp), dimension(:,:), allocatable :: temperature
   real(kind=wp), dimension(:), allocatable :: temperature_planck
   real(kind=wp) :: total_solar_irradiance
-  type(c_ptr) :: device_model = c_null_ptr   !< ecckd_model*, created lazily (tables packed once)
   contains
   procedure, public :: source_is_internal
   procedure, public :: source_is_external
@@ -66,8 +76,8 @@ type, extends(ty_gas_optics), public :: ty_gas_optics_ecckd
   procedure, public :: get_temp_max
   procedure, public :: gas_optics_int
   procedure, public :: gas_optics_ext
-  procedure, public :: finalize_load
-  procedure, public :: release_device
+  procedure, public :: finalize_load    !< optional: pack the tables now instead of at the first call
+  procedure, public :: release_device   !< optional: free the device model of these tables
 end type ty_gas_optics_ecckd
 
 
@@ -117,86 +127,237 @@ interface
     import :: c_ptr
     type(c_ptr), value :: model
   end subroutine
+end interface
+
+!> host-array entry points, generic over the kind of wp (include/ecckd_b200.h: ecckd_gas_optics_{lw,sw}_host_{f64,f32})
+interface ecckd_lw_host
   integer(c_int) function ecckd_gas_optics_lw_host_f64(model, ncol, nlay, plev, tlay, tlev, tsfc, ngas, names, vmr, &
       tau, lay_source, lev_source_inc, lev_source_dec, sfc_source, block_cols, err) bind(c, name="ecckd_gas_optics_lw_host_f64")
-    import :: c_int, c_ptr, c_char
-    type(c_ptr), value :: model, plev, tlay, tlev, tsfc, names, vmr, tau, lay_source, lev_source_inc, lev_source_dec, sfc_source
+    import :: c_int, c_ptr, c_char, c_double, ecckd_vmr_view
+    type(c_ptr), value :: model
     integer(c_int), value :: ncol, nlay, ngas, block_cols
+    real(c_double), dimension(*), intent(in) :: plev, tlay, tsfc
+    real(c_double), dimension(*), intent(in), optional :: tlev
+    type(c_ptr), dimension(*), intent(in) :: names
+    type(ecckd_vmr_view), dimension(*), intent(in) :: vmr
+    real(c_double), dimension(*), intent(inout) :: tau, lay_source, lev_source_inc, lev_source_dec, sfc_source
     character(kind=c_char) :: err(128)
   end function
+  integer(c_int) function ecckd_gas_optics_lw_host_f32(model, ncol, nlay, plev, tlay, tlev, tsfc, ngas, names, vmr, &
+      tau, lay_source, lev_source_inc, lev_source_dec, sfc_source, block_cols, err) bind(c, name="ecckd_gas_optics_lw_host_f32")
+    import :: c_int, c_ptr, c_char, c_float, ecckd_vmr_view
+    type(c_ptr), value :: model
+    integer(c_int), value :: ncol, nlay, ngas, block_cols
+    real(c_float), dimension(*), intent(in) :: plev, tlay, tsfc
+    real(c_float), dimension(*), intent(in), optional :: tlev
+    type(c_ptr), dimension(*), intent(in) :: names
+    type(ecckd_vmr_view), dimension(*), intent(in) :: vmr
+    real(c_float), dimension(*), intent(inout) :: tau, lay_source, lev_source_inc, lev_source_dec, sfc_source
+    character(kind=c_char) :: err(128)
+  end function
+end interface ecckd_lw_host
+
+interface ecckd_sw_host
   integer(c_int) function ecckd_gas_optics_sw_host_f64(model, ncol, nlay, plev, tlay, ngas, names, vmr, &
       tau, ssa, g, toa_src, block_cols, err) bind(c, name="ecckd_gas_optics_sw_host_f64")
-    import :: c_int, c_ptr, c_char
-    type(c_ptr), value :: model, plev, tlay, names, vmr, tau, ssa, g, toa_src
+    import :: c_int, c_ptr, c_char, c_double, ecckd_vmr_view
+    type(c_ptr), value :: model
     integer(c_int), value :: ncol, nlay, ngas, block_cols
+    real(c_double), dimension(*), intent(in) :: plev, tlay
+    type(c_ptr), dimension(*), intent(in) :: names
+    type(ecckd_vmr_view), dimension(*), intent(in) :: vmr
+    real(c_double), dimension(*), intent(inout) :: tau, toa_src
+    real(c_double), dimension(*), intent(inout), optional :: ssa, g
     character(kind=c_char) :: err(128)
   end function
-end interface
+  integer(c_int) function ecckd_gas_optics_sw_host_f32(model, ncol, nlay, plev, tlay, ngas, names, vmr, &
+      tau, ssa, g, toa_src, block_cols, err) bind(c, name="ecckd_gas_optics_sw_host_f32")
+    import :: c_int, c_ptr, c_char, c_float, ecckd_vmr_view
+    type(c_ptr), value :: model
+    integer(c_int), value :: ncol, nlay, ngas, block_cols
+    real(c_float), dimension(*), intent(in) :: plev, tlay
+    type(c_ptr), dimension(*), intent(in) :: names
+    type(ecckd_vmr_view), dimension(*), intent(in) :: vmr
+    real(c_float), dimension(*), intent(inout) :: tau, toa_src
+    real(c_float), dimension(*), intent(inout), optional :: ssa, g
+    character(kind=c_char) :: err(128)
+  end function
+end interface ecckd_sw_host
+
+
+! ---- device models, keyed on a signature of the tables (this is intent(in) in gas_optics) ---
+integer, parameter :: max_models = 16
+integer, parameter :: nsig = 6 + 3 * 16
+type :: cached_model
+  type(c_ptr) :: handle = c_null_ptr
+  real(kind=wp), dimension(nsig) :: sig = 0._wp
+end type cached_model
+type(cached_model), dimension(max_models), save :: cache
+integer, save :: ncached = 0
 
 
 contains
 
 
-!> @brief Pack the tables the loader filled and create the device model (idempotent).
-function finalize_load(this) result(error_msg)
-  class(ty_gas_optics_ecckd), intent(inout), target :: this
-  character(len=128) :: error_msg
+!> @brief O(num_gases) signature of the tables: extents, grid ends and a few entries of every table.
+pure function table_signature(this) result(sig)
+  class(ty_gas_optics_ecckd), intent(in) :: this
+  real(kind=wp), dimension(nsig) :: sig
+  integer :: i, n1, n2, n3, n4
 
+  sig(:) = 0._wp
+  sig(1) = merge(1._wp, 0._wp, this%shortwave)
+  sig(2) = real(size(this%gpoint_fraction, 2), wp)
+  sig(3) = real(size(this%log_pressure), wp) + 1000._wp * real(size(this%temperature, 2), wp)
+  sig(4) = real(this%num_gases, wp)
+  sig(5) = this%log_pressure(1) + this%log_pressure(size(this%log_pressure))
+  sig(6) = this%temperature(1, 1) + this%temperature(size(this%temperature, 1), size(this%temperature, 2))
+  do i = 1, this%num_gases
+    n1 = size(this%absorption(i)%coefficient, 1); n2 = size(this%absorption(i)%coefficient, 2)
+    n3 = size(this%absorption(i)%coefficient, 3); n4 = size(this%absorption(i)%coefficient, 4)
+    sig(6 + 3 * i - 2) = this%absorption(i)%coefficient(1, 1, 1, 1) + this%absorption(i)%coefficient(n1, n2, n3, n4)
+    sig(6 + 3 * i - 1) = this%absorption(i)%coefficient((n1 + 1) / 2, (n2 + 1) / 2, (n3 + 1) / 2, (n4 + 1) / 2)
+    sig(6 + 3 * i) = this%absorption(i)%reference_mole_fraction + real(this%absorption(i)%concentration_dependence_code, wp)
+  enddo
+end function table_signature
+
+
+!> @brief Handle of the device model of these tables; created (tables packed, uploaded) on first use.
+function device_model(this, error_msg) result(handle)
+  class(ty_gas_optics_ecckd), intent(in) :: this
+  character(len=128), intent(out) :: error_msg
+  type(c_ptr) :: handle
+
+  real(kind=wp), dimension(nsig) :: sig
+  integer :: i
+
+  error_msg = ""
+  handle = c_null_ptr
+  sig = table_signature(this)
+  !$omp critical (ecckd_b200_model_cache)
+  do i = 1, ncached
+    if (c_associated(cache(i)%handle) .and. all(cache(i)%sig .eq. sig)) then
+      handle = cache(i)%handle
+      exit
+    endif
+  enddo
+  if (.not. c_associated(handle)) then
+    if (ncached .ge. max_models) then
+      error_msg = "ecckd: more than 16 distinct ck models alive (release_device() frees one)"
+    else
+      handle = create_model(this, error_msg)
+      if (c_associated(handle)) then
+        ncached = ncached + 1
+        cache(ncached)%handle = handle
+        cache(ncached)%sig = sig
+      endif
+    endif
+  endif
+  !$omp end critical (ecckd_b200_model_cache)
+end function device_model
+
+
+!> @brief Pack the tables the loader filled (mo_load_coefficients.F90:46-144) and create the device model.
+!! The tables are copied into local TARGET arrays first: `this` has no TARGET attribute, and the
+!! library copies what it is given before returning.
+function create_model(this, error_msg) result(handle)
+  class(ty_gas_optics_ecckd), intent(in) :: this
+  character(len=128), intent(out) :: error_msg
+  type(c_ptr) :: handle
+
+  type :: gas_copy
+    real(c_double), dimension(:), allocatable :: coefficient, mole_fraction
+  end type gas_copy
+  type(gas_copy), dimension(16), target :: gc
+  real(c_double), dimension(:), allocatable, target :: log_pressure, temperature, temperature_planck, planck_function
+  real(c_double), dimension(:), allocatable, target :: rayleigh, solar
   type(ecckd_host_tables) :: t
   type(ecckd_gas_table), dimension(16), target :: g
   character(kind=c_char), dimension(128) :: err
   integer :: i, k, rc
 
   error_msg = ""
-  if (c_associated(this%device_model)) return
+  handle = c_null_ptr
+  log_pressure = real(this%log_pressure, c_double)
+  temperature = real(reshape(this%temperature, [size(this%temperature)]), c_double)
   t%shortwave = merge(1, 0, this%shortwave)
   t%ngpt = size(this%gpoint_fraction, 2)
   t%npress = size(this%log_pressure)
   t%ntemp = size(this%temperature, 2)
   t%nplanck = 0
   t%num_gases = this%num_gases
-  t%log_pressure = c_loc(this%log_pressure)
-  t%temperature = c_loc(this%temperature)
+  t%log_pressure = c_loc(log_pressure)
+  t%temperature = c_loc(temperature)
   t%temperature_planck = c_null_ptr; t%planck_function = c_null_ptr
   t%rayleigh_molar_scattering_coeff = c_null_ptr; t%solar_irradiance = c_null_ptr
   if (allocated(this%temperature_planck)) then
+    temperature_planck = real(this%temperature_planck, c_double)
+    planck_function = real(reshape(this%planck_function, [size(this%planck_function)]), c_double)
     t%nplanck = size(this%temperature_planck)
-    t%temperature_planck = c_loc(this%temperature_planck)
-    t%planck_function = c_loc(this%planck_function)
+    t%temperature_planck = c_loc(temperature_planck)
+    t%planck_function = c_loc(planck_function)
   endif
   if (allocated(this%solar_irradiance)) then
-    t%solar_irradiance = c_loc(this%solar_irradiance)
-    t%rayleigh_molar_scattering_coeff = c_loc(this%rayleigh_molar_scattering_coeff)
+    solar = real(this%solar_irradiance, c_double)
+    rayleigh = real(this%rayleigh_molar_scattering_coeff, c_double)
+    t%solar_irradiance = c_loc(solar)
+    t%rayleigh_molar_scattering_coeff = c_loc(rayleigh)
   endif
   do i = 1, this%num_gases
     do k = 1, 32
-      g(i)%name(k) = this%gas(i)(k:k)
+      g(i)%name(k) = this%gas(i)(k:k)                     ! blank-padded, as the loader leaves it
     enddo
     g(i)%composite_only = merge(1, 0, this%absorption(i)%composite_only)
     g(i)%concentration_dependence_code = this%absorption(i)%concentration_dependence_code
     g(i)%n_mole_fraction = 0
     g(i)%mole_fraction = c_null_ptr
     if (allocated(this%absorption(i)%mole_fraction)) then
+      gc(i)%mole_fraction = real(this%absorption(i)%mole_fraction, c_double)
       g(i)%n_mole_fraction = size(this%absorption(i)%mole_fraction)
-      g(i)%mole_fraction = c_loc(this%absorption(i)%mole_fraction)
+      g(i)%mole_fraction = c_loc(gc(i)%mole_fraction)
     endif
     g(i)%reserved = 0
     g(i)%reference_mole_fraction = this%absorption(i)%reference_mole_fraction
-    g(i)%coefficient = c_loc(this%absorption(i)%coefficient)
+    gc(i)%coefficient = real(reshape(this%absorption(i)%coefficient, [size(this%absorption(i)%coefficient)]), c_double)
+    g(i)%coefficient = c_loc(gc(i)%coefficient)
   enddo
   t%gas = c_loc(g)
   t%nband = 0; t%reserved = 0
   t%band_lims_wvn = c_null_ptr; t%band2gpt = c_null_ptr      ! kept by the inherited ty_optical_props%init
-  rc = ecckd_model_create(t, 1, c_null_ptr, this%device_model, err)
-  if (rc .ne. 0) call c_to_f_string(err, error_msg)
+  rc = ecckd_model_create(t, 1, c_null_ptr, handle, err)
+  if (rc .ne. 0) then
+    call c_to_f_string(err, error_msg)
+    handle = c_null_ptr
+  endif
+end function create_model
+
+
+!> @brief Optional: create the device model now (idempotent; gas_optics does it on first use otherwise).
+function finalize_load(this) result(error_msg)
+  class(ty_gas_optics_ecckd), intent(in) :: this
+  character(len=128) :: error_msg
+  type(c_ptr) :: handle
+  handle = device_model(this, error_msg)
 end function finalize_load
 
 
-!> @brief Free the device model.
+!> @brief Free the device model of these tables (if any).
 subroutine release_device(this)
-  class(ty_gas_optics_ecckd), intent(inout) :: this
-  if (c_associated(this%device_model)) call ecckd_model_destroy(this%device_model)
-  this%device_model = c_null_ptr
+  class(ty_gas_optics_ecckd), intent(in) :: this
+  real(kind=wp), dimension(nsig) :: sig
+  integer :: i
+  sig = table_signature(this)
+  !$omp critical (ecckd_b200_model_cache)
+  do i = 1, ncached
+    if (c_associated(cache(i)%handle) .and. all(cache(i)%sig .eq. sig)) then
+      call ecckd_model_destroy(cache(i)%handle)
+      cache(i) = cache(ncached)
+      cache(ncached)%handle = c_null_ptr
+      ncached = ncached - 1
+      exit
+    endif
+  enddo
+  !$omp end critical (ecckd_b200_model_cache)
 end subroutine release_device
 
 
@@ -206,26 +367,30 @@ end subroutine release_device
 function marshal_gases(gas_desc, ncol, nlay, names, name_ptrs, views, vmr, ngas) result(error_msg)
   type(ty_gas_concs), intent(in) :: gas_desc
   integer, intent(in) :: ncol, nlay
-  character(kind=c_char, len=33), dimension(:), allocatable, target, intent(out) :: names
-  type(c_ptr), dimension(:), allocatable, target, intent(out) :: name_ptrs
-  type(ecckd_vmr_view), dimension(:), allocatable, target, intent(out) :: views
+  character(kind=c_char), dimension(:,:), allocatable, target, intent(out) :: names   ! (33, ngas), NUL-terminated
+  type(c_ptr), dimension(:), allocatable, intent(out) :: name_ptrs
+  type(ecckd_vmr_view), dimension(:), allocatable, intent(out) :: views
   real(kind=wp), dimension(:,:,:), allocatable, target, intent(out) :: vmr
   integer, intent(out) :: ngas
   character(len=128) :: error_msg
 
   character(len=32), dimension(:), allocatable :: gas_names
-  integer :: j
+  integer :: j, k, n
 
   error_msg = ""
   ngas = gas_desc%get_num_gases()
-  allocate(gas_names(ngas), names(ngas), name_ptrs(ngas), views(ngas), vmr(ncol, nlay, ngas))
+  allocate(gas_names(ngas), names(33, ngas), name_ptrs(ngas), views(ngas), vmr(ncol, nlay, ngas))
   gas_names = gas_desc%get_gas_names()
   do j = 1, ngas
-    names(j) = trim(gas_names(j))//c_null_char
-    name_ptrs(j) = c_loc(names(j))
+    n = len_trim(gas_names(j))
+    do k = 1, 33
+      names(k, j) = c_null_char
+      if (k .le. n) names(k, j) = gas_names(j)(k:k)
+    enddo
+    name_ptrs(j) = c_loc(names(1, j))
     error_msg = gas_desc%get_vmr(gas_names(j), vmr(:,:,j))
     if (trim(error_msg) .ne. "") return
-    views(j)%ptr = c_loc(vmr(1,1,j))
+    views(j)%ptr = c_loc(vmr(1, 1, j))
     if (minval(vmr(:,:,j)) .eq. maxval(vmr(:,:,j))) then
       views(j)%col_stride = 0; views(j)%lay_stride = 0
     else
@@ -252,34 +417,25 @@ function gas_optics_int(this, play, plev, tlay, tsfc, gas_desc, &
   real(kind=wp), dimension(:,:), intent(in), target, optional :: col_dry
   real(kind=wp), dimension(:,:), intent(in), target, optional :: tlev
 
-  character(kind=c_char, len=33), dimension(:), allocatable, target :: names
-  type(c_ptr), dimension(:), allocatable, target :: name_ptrs
-  type(ecckd_vmr_view), dimension(:), allocatable, target :: views
+  character(kind=c_char), dimension(:,:), allocatable, target :: names
+  type(c_ptr), dimension(:), allocatable :: name_ptrs
+  type(ecckd_vmr_view), dimension(:), allocatable :: views
   real(kind=wp), dimension(:,:,:), allocatable, target :: vmr
-  real(kind=wp), dimension(:,:), allocatable, target :: plev_c, tlay_c, tlev_c
-  real(kind=wp), dimension(:), allocatable, target :: tsfc_c
   character(kind=c_char), dimension(128) :: err
-  type(c_ptr) :: tlev_ptr
+  type(c_ptr) :: model
   integer :: ncol, nlay, ngas, rc
 
-  if (.not. c_associated(this%device_model)) then
-    error_msg = "ecckd: call finalize_load() after load_and_init (device tables not packed)"
-    return
-  endif
+  model = device_model(this, error_msg)
+  if (.not. c_associated(model)) return
   ncol = size(tlay, 1); nlay = size(tlay, 2)
   error_msg = marshal_gases(gas_desc, ncol, nlay, names, name_ptrs, views, vmr, ngas)
   if (len_trim(error_msg) .gt. 0) return
-  plev_c = plev; tlay_c = tlay; tsfc_c = tsfc            ! contiguous copies (assumed-shape dummies may be strided)
-  tlev_ptr = c_null_ptr
-  if (present(tlev)) then
-    tlev_c = tlev
-    tlev_ptr = c_loc(tlev_c)
-  endif
-  rc = ecckd_gas_optics_lw_host_f64(this%device_model, ncol, nlay, c_loc(plev_c), c_loc(tlay_c), tlev_ptr, c_loc(tsfc_c), &
-         ngas, c_loc(name_ptrs), c_loc(views), c_loc(optical_props%tau), c_loc(sources%lay_source), &
-         c_loc(sources%lev_source_inc), c_loc(sources%lev_source_dec), c_loc(sources%sfc_source), 0, err)
+  ! tlev is forwarded as it is: an absent optional becomes NULL, and the library then returns the
+  ! reference's "tlev is required for ecckd" (:415) after writing tau, lay_source and sfc_source
+  rc = ecckd_lw_host(model, ncol, nlay, plev, tlay, tlev, tsfc, ngas, name_ptrs, views, optical_props%tau, &
+                     sources%lay_source, sources%lev_source_inc, sources%lev_source_dec, sources%sfc_source, 0, err)
   error_msg = ""
-  if (rc .ne. 0) call c_to_f_string(err, error_msg)       ! e.g. "tlev is required for ecckd" (reference :415)
+  if (rc .ne. 0) call c_to_f_string(err, error_msg)
 end function gas_optics_int
 
 
@@ -293,41 +449,33 @@ function gas_optics_ext(this, play, plev, tlay, gas_desc, optical_props, toa_src
   real(kind=wp), dimension(:,:), intent(in) :: tlay
   type(ty_gas_concs), intent(in) :: gas_desc
   class(ty_optical_props_arry), intent(inout) :: optical_props
-  real(kind=wp), dimension(:,:), intent(out), target :: toa_src
+  real(kind=wp), dimension(:,:), intent(out) :: toa_src
   real(kind=wp), dimension(:,:), intent(in), target, optional :: col_dry
   character(len=128) :: error_msg
 
-  character(kind=c_char, len=33), dimension(:), allocatable, target :: names
-  type(c_ptr), dimension(:), allocatable, target :: name_ptrs
-  type(ecckd_vmr_view), dimension(:), allocatable, target :: views
+  character(kind=c_char), dimension(:,:), allocatable, target :: names
+  type(c_ptr), dimension(:), allocatable :: name_ptrs
+  type(ecckd_vmr_view), dimension(:), allocatable :: views
   real(kind=wp), dimension(:,:,:), allocatable, target :: vmr
-  real(kind=wp), dimension(:,:), allocatable, target :: plev_c, tlay_c, toa_c
   character(kind=c_char), dimension(128) :: err
-  type(c_ptr) :: ssa_ptr, g_ptr
+  type(c_ptr) :: model
   integer :: ncol, nlay, ngas, rc
 
-  if (.not. c_associated(this%device_model)) then
-    error_msg = "ecckd: call finalize_load() after load_and_init (device tables not packed)"
-    return
-  endif
+  model = device_model(this, error_msg)
+  if (.not. c_associated(model)) return
   ncol = size(tlay, 1); nlay = size(tlay, 2)
   error_msg = marshal_gases(gas_desc, ncol, nlay, names, name_ptrs, views, vmr, ngas)
   if (len_trim(error_msg) .gt. 0) return
-  plev_c = plev; tlay_c = tlay
-  allocate(toa_c(ncol, size(toa_src, 2)))
-  ssa_ptr = c_null_ptr; g_ptr = c_null_ptr
   select type(optical_props)
     type is (ty_optical_props_2str)
-      ssa_ptr = c_loc(optical_props%ssa); g_ptr = c_loc(optical_props%g)
-  end select                                              ! not 2str: the library returns the reference's error (:462)
-  rc = ecckd_gas_optics_sw_host_f64(this%device_model, ncol, nlay, c_loc(plev_c), c_loc(tlay_c), ngas, c_loc(name_ptrs), &
-         c_loc(views), c_loc(optical_props%tau), ssa_ptr, g_ptr, c_loc(toa_c), 0, err)
+      rc = ecckd_sw_host(model, ncol, nlay, plev, tlay, ngas, name_ptrs, views, optical_props%tau, &
+                         optical_props%ssa, optical_props%g, toa_src, 0, err)
+    class default      ! ssa, g absent -> NULL: tau is written, then the reference's error (:462) comes back
+      rc = ecckd_sw_host(model, ncol, nlay, plev, tlay, ngas, name_ptrs, views, optical_props%tau, &
+                         toa_src=toa_src, block_cols=0, err=err)
+  end select
   error_msg = ""
-  if (rc .ne. 0) then
-    call c_to_f_string(err, error_msg)
-    return
-  endif
-  toa_src(:,:) = toa_c(:,:)
+  if (rc .ne. 0) call c_to_f_string(err, error_msg)
 end function gas_optics_ext
 
 

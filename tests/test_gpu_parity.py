@@ -372,17 +372,22 @@ def test_persistent_blocks_with_ragged_last_chunk(ncol, dev, gpu_models, ck_mode
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
-def test_persistent_blocks_with_several_varying_gases(dtype, dev, gpu_models, ck_models, c_oracles):
-    """More than one bilinear gas varying over the call selects the 8-slot instantiation (8-column tiles, writer
-    warps); 9470 columns put it into the persistent two-tile-chunk geometry (1184 tiles, the last one ragged)."""
-    ncol, nlay = 9470, 3
+@pytest.mark.parametrize("varying", [("co2",), ("co2", "ch4"), ("co2", "ch4", "n2o"), ("co2", "ch4", "n2o", "cfc11", "cfc12", "o2")],
+                         ids=["nvar2", "nvar3", "nvar4", "nvar7"])
+def test_persistent_blocks_with_several_varying_gases(varying, dtype, dev, gpu_models, ck_models, c_oracles):
+    """Bilinear gases given as (ncol, nlay) fields instead of scalars (co2 / ch4 / n2o profiles, or everything as a field
+    like a host model that never passes scalars): with o3 that is nvar = 2, 3 (the quad kernel's three-gas
+    instantiation), 4 and 7 (the 8-slot column-walk instantiation).  9472 columns: several tiles per persistent block.
+    ch4 / n2o wobble across their reference mole fractions, so the per-gas clamp (:233-238) fires in part of the cells."""
+    ncol, nlay = 9472, 3
     plev, tlay, tlev, tsfc, gases = atm_numpy(synthetic.make_atmosphere(ncol, nlay))
     wobble = 1 + 0.2 * np.cos(np.arange(tlay.size)).reshape(tlay.shape, order="F")
-    gl = [(n, v if isinstance(v, np.ndarray) else (np.asfortranarray(v * wobble) if n in ("co2", "ch4", "n2o") else v))
-          for n, v in gases]
+    gl = [(n, v if isinstance(v, np.ndarray) else (np.asfortranarray(v * wobble) if n in varying else v)) for n, v in gases]
     for key in ("lw_fsck", "sw_wide"):
-        out = run_gpu(gpu_models[key], plev, tlay, tlev, tsfc, gl, dtype, dev, ecckd_b200.KERNEL_WALK)
-        check(out, run_oracle(c_oracles[key], ck_models[key], plev, tlay, tlev, tsfc, gl, dtype), TOL[dtype], f"{key}/nvar=4")
+        ref = run_oracle(c_oracles[key], ck_models[key], plev, tlay, tlev, tsfc, gl, dtype)
+        for kern in (ecckd_b200.KERNEL_WALK, ecckd_b200.KERNEL_COLWALK):
+            out = run_gpu(gpu_models[key], plev, tlay, tlev, tsfc, gl, dtype, dev, kern)
+            check(out, ref, TOL[dtype], f"{key}/varying={varying}/kernel={kern}")
 
 
 def test_linearity_in_a_linear_gas(dev, gpu_models):
