@@ -70,7 +70,7 @@ def test_gpoint_count_sweep(key, ngpt, dtype, dev, ck_models):
     m = share_composite(regrid_g(ck_models[key], ngpt))
     go = ecckd_b200.GasOpticsEcckd.from_components(m)
     assert go.get_ngpt() == ngpt and go.get_nband() == 0
-    inp = atm_numpy(synthetic.make_atmosphere(66, 45))
+    inp = atm_numpy(synthetic.make_atmosphere(68, 45))      # a multiple of 4: quad-eligible in fp32 too
     ref = run_oracle(oracle_for(m), m, *inp, dtype)
     for kern in (ecckd_b200.KERNEL_QUAD, ecckd_b200.KERNEL_COLWALK, ecckd_b200.KERNEL_GENERIC):
         check(run_gpu(go, *inp, dtype, dev, kern), ref, TOL[dtype], f"{key} ngpt={ngpt} kernel={kern}")
