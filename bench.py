@@ -15,9 +15,15 @@ go through a ring of two column-block output buffers, as a host model consumes t
 `value`  : whole-job g-point-layers/s, device-resident arrays, CUDA events, max over ranks.
 `e2e`    : the same rate through the host-array C-ABI entry points (ecckd_gas_optics_{lw,sw}_host_f64):
            pinned host inputs -> H2D -> kernels -> D2H of every output, all inside the timed region.
-`roofline`: LW walking kernel, algorithmic bytes / CUDA-event duration vs the measured HBM copy bandwidth.
+`roofline`: LW quad kernel (roofline_sw: SW; roofline_f32 / roofline_sw_f32: the fp32 variant of configs[3]),
+           algorithmic bytes / CUDA-event duration vs the measured HBM copy bandwidth.
 `cpu_baseline` / --impl reference: oracle/ecckd_oracle.c (-O3 -march=native, all host threads) -- a port:
-           the Fortran reference cannot be built offline (no Fortran compiler, netCDF-Fortran, rte-rrtmgp).
+           the Fortran reference cannot be built offline (no Fortran compiler here; `cpu_baseline.fortran` records
+           whether the box running the bench has one -- oracle/ref is the recipe that would then pin and time it).
+`extras`  : RFMIP-shaped call latencies (configs[0-2]: 1 / 100 / 1800 columns x 60 layers, device and host path, with the
+           CPU port's time for the same call), calls with co2/ch4/n2o as profiles, the generic and column-walk kernels,
+           the host path on pageable memory.
+--total-cols N: BASELINE configs[4] as named -- N columns (6.6M) column-sharded over the GPUs, strong scaling.
 """
 from __future__ import annotations
 
@@ -175,11 +181,90 @@ def run_reference(args, rank: int, world: int) -> None:
                    "columns_per_step": ncol, "nlay": NLAY, "ngpt_lw": NG_LW, "ngpt_sw": NG_SW,
                    "note": "CPU restatement (oracle/ecckd_oracle.c, -O3 -march=native) of src/gas_optics_ecckd.f90; the Fortran "
                            "reference itself cannot be built offline (no Fortran compiler / netCDF-Fortran / rte-rrtmgp)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "fortran": fortran_probe()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total,
     }
     print(json.dumps(line))
+
+
+def fortran_probe() -> dict:
+    """Is there a Fortran compiler on THIS box (probe at run time)?  With one, `make -C oracle/ref` builds the
+    unmodified reference against stub rte-rrtmgp modules -- but only next to /root/reference, which the GPU box lacks."""
+    from oracle.ref import run_ref
+    fc = run_ref.fortran_compiler()
+    return {"compiler": fc, "reference_tree": os.path.isdir(run_ref.REFERENCE), "ref_driver_built": os.path.exists(run_ref.DRIVER)}
+
+
+def rfmip_latencies(dev) -> dict:
+    """BASELINE configs[0-2] (RFMIP-shaped synthetic: the RFMIP file is not available offline): microseconds per
+    gas_optics call of 1 / 100 / 1800 columns x 60 layers for the three ck files -- device arrays (CUDA events over
+    back-to-back calls), host arrays through the host entry points (wall clock), and the CPU port on one thread (the
+    reference drivers run block_size = 1 on one thread, ecckd_rfmip_lw.F90:39,107) for the same call."""
+    import torch
+    import ecckd_b200
+    from ecckd_b200 import synthetic
+    from oracle import ckd_model
+    from oracle.c_oracle import COracle
+    files = {"lw_fsck-tol0.0161": LW_FILE, "lw_rrtmgp-tol0.061": os.path.join(DATA, "ecckd-1.2_lw_ckd-definition_climate_rrtmgp-tol0.061.nc"),
+             "sw_wide-tol0.05": SW_FILE}
+    exps = synthetic.make_rfmip_like()                       # 18 experiments x 100 columns x 60 layers
+    out = {}
+    for label, path in files.items():
+        go = ecckd_b200.GasOpticsEcckd.load(path, devices=[dev.index or 0])
+        lw_ = go.source_is_internal()
+        co = COracle(ckd_model.load_and_init(path), fast=True)
+        res = {}
+        for ncol in (1, 100, 1800):
+            if ncol <= 100:
+                a = exps[5]
+                sel = lambda t: t[:ncol].contiguous() if t.dim() == 1 else ecckd_b200.to_fortran(t[:ncol], torch.float64)
+                plev, tlay, tlev, tsfc = sel(a.plev), sel(a.tlay), sel(a.tlev), sel(a.tsfc)
+                gl = [(n, sel(v) if torch.is_tensor(v) else v) for n, v in a.gas_list()]
+            else:                                            # all experiments in one call: scalars differ per experiment -> use experiment 5's
+                cat = lambda k: ecckd_b200.to_fortran(torch.cat([getattr(e, k) for e in exps], 0), torch.float64)
+                plev, tlay, tlev = cat("plev"), cat("tlay"), cat("tlev")
+                tsfc = torch.cat([e.tsfc for e in exps], 0)
+                gl = [(n, (cat(n) if torch.is_tensor(v) else v)) for n, v in exps[5].gas_list()]
+            F = lambda t: np.asfortranarray(t.numpy())
+            gl_np = [(n, F(v) if torch.is_tensor(v) else v) for n, v in gl]
+            D = lambda t: ecckd_b200.to_fortran(t, torch.float64, dev)
+            gd = ecckd_b200.PreparedGases([(n, D(v) if torch.is_tensor(v) else v) for n, v in gl], ncol, 60, np.float64, dev)
+            dp, dt_, dl, ds = D(plev), D(tlay), D(tlev), tsfc.to(dev)
+            o = None
+            call = lambda: go.gas_optics(None, dp, dt_, ds if lw_ else None, gd, tlev=dl if lw_ else None, out=o)
+            for _ in range(20):
+                o = call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_rep = 200
+            e0.record()
+            for _ in range(n_rep):
+                o = call()
+            e1.record(); torch.cuda.synchronize()
+            dev_us = e0.elapsed_time(e1) * 1e3 / n_rep
+            gh = ecckd_b200.PreparedGases(gl_np, ncol, 60, np.float64, None)
+            hp, ht, hl, hs = F(plev), F(tlay), F(tlev), tsfc.numpy()
+            oh = None
+            hcall = lambda: go.gas_optics(None, hp, ht, hs if lw_ else None, gh, tlev=hl if lw_ else None, out=oh)
+            for _ in range(5):
+                oh = hcall()
+            w0 = time.perf_counter()
+            for _ in range(50):
+                oh = hcall()
+            host_us = (time.perf_counter() - w0) * 1e6 / 50
+            w0 = time.perf_counter()
+            n_cpu = 3 if ncol > 100 else 20
+            for _ in range(n_cpu):
+                (co.gas_optics_int(hp, ht, hs, gl_np, hl) if lw_ else co.gas_optics_ext(hp, ht, gl_np))
+            cpu_us = (time.perf_counter() - w0) * 1e6 / n_cpu
+            res[f"ncol{ncol}"] = {"device_us": dev_us, "host_path_us": host_us, "cpu_port_1thread_us": cpu_us}
+        out[label] = res
+        go.close()
+    out["note"] = ("per gas_optics call through the Python binding; device_us = CUDA events over 200 back-to-back calls on device arrays; "
+                   "host_path_us = wall clock of the synchronous host entry point on pageable numpy arrays (H2D + kernels + D2H); "
+                   "cpu_port_1thread_us = oracle/ecckd_oracle.c -O3 on one thread, as the reference drivers run")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -195,6 +280,9 @@ def main() -> None:
     ap.add_argument("--e2e-block", type=int, default=1 << 14)
     ap.add_argument("--cpu-cols", type=int, default=1 << 19, help="bounded sample for cpu_baseline")
     ap.add_argument("--ref-cols", type=int, default=1 << 15, help="columns per step of --impl reference")
+    ap.add_argument("--total-cols", type=int, default=0,
+                    help="strong scaling: this many columns in total, column-sharded over the GPUs (configs[4]: 6600000)")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -217,9 +305,14 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
 
-    ncol, B = args.cols, min(args.block, args.cols)
+    if args.total_cols > 0:                     # strong scaling: contiguous shards of one global grid (configs[4])
+        col_base, c1 = sharding.shard_columns(args.total_cols, world, rank)
+        ncol = c1 - col_base
+        ncol_all = args.total_cols
+    else:                                       # weak scaling: every GPU owns its own `cols` columns of the global grid
+        ncol, col_base, ncol_all = args.cols, rank * args.cols, args.cols * world
+    B = min(args.block, ncol)
     nblk = (ncol + B - 1) // B
-    col_base = rank * ncol                      # weak scaling: every GPU owns its own `cols` columns of the global grid
     lw = ecckd_b200.GasOpticsEcckd.load(LW_FILE, devices=[local_rank])
     sw = ecckd_b200.GasOpticsEcckd.load(SW_FILE, devices=[local_rank])
 
@@ -271,7 +364,7 @@ def main() -> None:
     sharding.barrier()
     clocks = sampler.stop() if sampler else None
     ms_step = sharding.max_over_ranks(t0.elapsed_time(t1) / args.steps, dev)
-    gptl_step = ncol * NLAY * (NG_LW + NG_SW) * world
+    gptl_step = ncol_all * NLAY * (NG_LW + NG_SW)
     value = gptl_step / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (LW walk): live CUDA-event durations of every timed launch -
@@ -281,43 +374,89 @@ def main() -> None:
     bytes_lw = algorithmic_bytes(B, NLAY, NG_LW, True)
     achieved = bytes_lw / (lw_ms * 1e-3) / 1e9
     traffic = profiled_traffic()
-    roofline = {"bound": "hbm", "kernel": "ecckd::walk_kernel<double, LW> (+ per-call table-mix kernel, <1% of the time)",
+    roofline = {"bound": "hbm", "kernel": "ecckd::quad_kernel<double, LW> (+ per-call table-mix kernel, <1% of the time)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic["lw_dram_bytes_per_column"] * B if traffic else None),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture "
+                                  "(profiles/traffic.json), scaled per column -- not re-measured in this run",
                 "algorithmic_bytes_per_launch": bytes_lw, "columns_per_launch": B, "ms_per_launch": lw_ms, "peak_source": peak_src}
     fsw = [(a.elapsed_time(bb), n) for a, bb, n in ev_pairs["sw"] if n == B]
     sw_ms = statistics.mean(t for t, _ in fsw) if fsw else float("nan")
     bytes_sw = algorithmic_bytes(B, NLAY, NG_SW, False)
-    roofline_sw = {"bound": "hbm", "kernel": "ecckd::walk_kernel<double, SW>", "achieved": bytes_sw / (sw_ms * 1e-3) / 1e9, "peak": peak,
+    roofline_sw = {"bound": "hbm", "kernel": "ecckd::quad_kernel<double, SW>", "achieved": bytes_sw / (sw_ms * 1e-3) / 1e9, "peak": peak,
                    "unit": "GB/s", "frac": bytes_sw / (sw_ms * 1e-3) / 1e9 / peak, "traffic": (traffic["sw_dram_bytes_per_column"] * B if traffic else None),
                    "ms_per_launch": sw_ms}
     launches = args.steps * nblk * 4          # per block: LW mix + LW walk + SW mix + SW walk
 
-    # ---- extras (not part of the headline): the fp32 variant on one launch-sized block ------------------
+    # ---- the fp32 variant of configs[3] ("fp64 and fp32"): same blocks, same kernels, CUDA events per launch ----------
     extras = {}
+    roofline_f32 = roofline_sw_f32 = None
     try:
         atm32 = blocks[0][0].astype(torch.float32)
         g32 = ecckd_b200.PreparedGases(atm32.gas_list(), atm32.ncol, NLAY, np.float32, dev)
         o_lw = o_sw = None
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        for rep in range(4):
-            if rep == 3:
-                ev[0].record()
+        t_lw, t_sw = [], []
+        for rep_ in range(3 + 5):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
             o_lw = lw.gas_optics(None, atm32.plev, atm32.tlay, atm32.tsfc, g32, tlev=atm32.tlev, out=o_lw)
-            if rep == 3:
-                ev[1].record()
+            ev[1].record()
             o_sw = sw.gas_optics(None, atm32.plev, atm32.tlay, None, g32, out=o_sw)
-            if rep == 3:
-                ev[2].record()
-        torch.cuda.synchronize()
-        t_lw, t_sw = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-        extras["f32"] = {"columns": atm32.ncol, "lw_ms": t_lw, "sw_ms": t_sw,
-                         "gptl_per_s": atm32.ncol * NLAY * (NG_LW + NG_SW) / ((t_lw + t_sw) * 1e-3),
-                         "lw_frac_of_hbm": algorithmic_bytes(atm32.ncol, NLAY, NG_LW, True, 4) / (t_lw * 1e-3) / 1e9 / peak,
-                         "sw_frac_of_hbm": algorithmic_bytes(atm32.ncol, NLAY, NG_SW, False, 4) / (t_sw * 1e-3) / 1e9 / peak}
+            ev[2].record()
+            torch.cuda.synchronize()
+            if rep_ >= 3:
+                t_lw.append(ev[0].elapsed_time(ev[1])); t_sw.append(ev[1].elapsed_time(ev[2]))
+        m_lw, m_sw = statistics.mean(t_lw), statistics.mean(t_sw)
+        b_lw, b_sw = algorithmic_bytes(atm32.ncol, NLAY, NG_LW, True, 4), algorithmic_bytes(atm32.ncol, NLAY, NG_SW, False, 4)
+        roofline_f32 = {"bound": "hbm", "kernel": "ecckd::quad_kernel<float, LW>", "achieved": b_lw / (m_lw * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": b_lw / (m_lw * 1e-3) / 1e9 / peak, "traffic": None, "ms_per_launch": m_lw, "columns_per_launch": atm32.ncol,
+                        "algorithmic_bytes_per_launch": b_lw, "gptl_per_s": atm32.ncol * NLAY * NG_LW / (m_lw * 1e-3)}
+        roofline_sw_f32 = {"bound": "hbm", "kernel": "ecckd::quad_kernel<float, SW>", "achieved": b_sw / (m_sw * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": b_sw / (m_sw * 1e-3) / 1e9 / peak, "traffic": None, "ms_per_launch": m_sw, "columns_per_launch": atm32.ncol,
+                           "algorithmic_bytes_per_launch": b_sw, "gptl_per_s": atm32.ncol * NLAY * NG_SW / (m_sw * 1e-3)}
+        extras["f32"] = {"columns": atm32.ncol, "lw_ms": m_lw, "sw_ms": m_sw, "gptl_per_s": atm32.ncol * NLAY * (NG_LW + NG_SW) / ((m_lw + m_sw) * 1e-3)}
         del atm32, g32, o_lw, o_sw
     except Exception as exc:   # extras must never break the headline line
         extras["f32_error"] = str(exc)
+
+    # ---- extras: other instantiations and kernels on one launch-sized block (fp64, CUDA events, mean of 3) -----------
+    def timed_call(go, atm, gases, lw_, kernel=ecckd_b200.KERNEL_AUTO, reps=3):
+        out, ts = None, []
+        for r_ in range(2 + reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc if lw_ else None, gases, tlev=atm.tlev if lw_ else None, kernel=kernel, out=out)
+            e1.record(); torch.cuda.synchronize()
+            if r_ >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.mean(ts)
+    if rank == 0 and not args.no_extras:
+        try:
+            atm0 = blocks[0][0]
+            nb0 = atm0.ncol
+            wob = 1.0 + 0.2 * torch.cos(torch.arange(nb0 * NLAY, device=dev, dtype=torch.float64)).reshape(NLAY, nb0).t()
+            for label, names in (("co2_ch4_n2o_profiles", ("co2", "ch4", "n2o")), ("all_gases_as_fields", ("co2", "ch4", "n2o", "o2", "cfc11", "cfc12"))):
+                gl = [(n, (v if torch.is_tensor(v) else (ecckd_b200.to_fortran(v * wob, torch.float64, dev) if n in names else v))) for n, v in atm0.gas_list()]
+                gv = ecckd_b200.PreparedGases(gl, nb0, NLAY, np.float64, dev)
+                extras[label] = {"lw_ms": timed_call(lw, atm0, gv, True), "sw_ms": timed_call(sw, atm0, gv, False), "columns": nb0,
+                                 "note": "nvar = %d varying bilinear gases (+ the h2o look-up table)" % (len(names) + 1)}
+                del gl, gv
+            g0_ = blocks[0][1]
+            extras["generic_kernel"] = {"lw_ms": timed_call(lw, atm0, g0_, True, ecckd_b200.KERNEL_GENERIC), "sw_ms": timed_call(sw, atm0, g0_, False, ecckd_b200.KERNEL_GENERIC), "columns": nb0}
+            extras["column_walk_kernel"] = {"lw_ms": timed_call(lw, atm0, g0_, True, ecckd_b200.KERNEL_COLWALK), "sw_ms": timed_call(sw, atm0, g0_, False, ecckd_b200.KERNEL_COLWALK),
+                                            "columns": nb0, "note": "round-1 product kernel, now the fallback for column counts without a 16-byte layer pitch"}
+            nodd = nb0 - 1
+            atm_odd = synthetic.make_atmosphere(nodd, NLAY, col0=col_base, device=dev)
+            g_odd = ecckd_b200.PreparedGases(atm_odd.gas_list(), nodd, NLAY, np.float64, dev)
+            extras["odd_ncol"] = {"lw_ms": timed_call(lw, atm_odd, g_odd, True), "sw_ms": timed_call(sw, atm_odd, g_odd, False), "columns": nodd,
+                                  "note": "device-pointer call with an odd column count: no tensor map possible, column-walk kernel with writer warps"}
+            del atm_odd, g_odd
+        except Exception as exc:
+            extras["kernels_error"] = str(exc)
+        try:
+            extras["rfmip"] = rfmip_latencies(dev)
+        except Exception as exc:
+            extras["rfmip_error"] = str(exc)
 
     # free the device-resident workload before the host-array measurement
     del blocks, ring
@@ -370,26 +509,55 @@ def main() -> None:
                "api": "ecckd_gas_optics_{lw,sw}_host_f64 (pinned host arrays, H2D + kernels + D2H per column block; the caller blocks "
                       "its columns like the reference driver, so every copy is contiguous)",
                "pcie_d2h_GBps": d2h / dt / 1e9}
+        if rank == 0 and not args.no_extras:
+            try:    # the same step on PAGEABLE host arrays (what a Fortran host model passes; the library page-locks them per call)
+                pg = lambda a: np.asfortranarray(np.array(a))
+                pblocks = []
+                for nb, h, _ in hblocks[:2]:
+                    hpg = {k: pg(v) for k, v in h.items()}
+                    gl = [(n, (hpg[n] if n in ("h2o", "o3") else v)) for n, v in synthetic.make_atmosphere(1, NLAY).gas_list()]
+                    pblocks.append((nb, hpg, ecckd_b200.PreparedGases(gl, nb, NLAY, np.float64, None)))
+                pout = {"lw": {k: pg(v) for k, v in hout["lw"].items()}, "sw": {k: pg(v) for k, v in hout["sw"].items()}}
+
+                def pstep():
+                    for nb, h, gases in pblocks:
+                        lw.gas_optics(None, h["plev"], h["tlay"], h["tsfc"], gases, tlev=h["tlev"], out=pout["lw"] if nb == EB else None, block_cols=EB)
+                        sw.gas_optics(None, h["plev"], h["tlay"], None, gases, out=pout["sw"] if nb == EB else None, block_cols=EB)
+                pstep()
+                w0 = time.perf_counter()
+                for _ in range(2):
+                    pstep()
+                pdt = (time.perf_counter() - w0) / 2
+                pcols = sum(nb for nb, _, _ in pblocks)
+                extras["e2e_pageable"] = {"value": pcols * NLAY * (NG_LW + NG_SW) / pdt, "unit": UNIT, "columns_per_step": pcols,
+                                          "note": "host entry points on pageable (malloc'd) arrays; arrays >= 8 MiB are page-locked in place for the call"}
+                del pblocks, pout
+            except Exception as exc:
+                extras["e2e_pageable_error"] = str(exc)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, secs, threads = cpu_port_rate(args.cpu_cols, 0)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "fortran": fortran_probe(),
                "sample": f"{args.cpu_cols} of the same synthetic columns x {NLAY} layers, LW+SW, {secs:.1f} s on {threads} threads "
                          "(oracle/ecckd_oracle.c -O3 -march=native; Fortran reference not buildable offline)"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic GCM block, 1M columns x 137 layers, LW+SW on 1 B200, fp64 (BASELINE.json configs[3]); "
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.total_cols > 0 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": ("synthetic global grid, %d columns x 137 layers, LW+SW column-sharded over the GPUs, fp64 (BASELINE.json configs[4])" % args.total_cols)
+                                   if args.total_cols > 0 else
+                                   "synthetic GCM block, 1M columns x 137 layers, LW+SW on 1 B200, fp64 (BASELINE.json configs[3]); "
                                    "N GPUs = N x 1M columns column-sharded, no collective",
                        "columns_per_gpu": ncol, "nlay": NLAY, "ngpt_lw": NG_LW, "ngpt_sw": NG_SW, "columns_per_launch": B,
                        "ck_definitions": [os.path.basename(LW_FILE), os.path.basename(SW_FILE)],
                        "l2": "every launch streams >9 GB of outputs and 0.36 GB of inputs: far larger than the 126 MB L2, no flush needed",
                        "gases": "h2o, o3 (ncol,nlay) fields; co2, ch4, n2o, o2, cfc11, cfc12 scalars (RFMIP convention)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_sw": roofline_sw,
+            "roofline_f32": roofline_f32, "roofline_sw_f32": roofline_sw_f32,
             "cpu_baseline": cpu, "extras": extras,
             "split": {"lw_gptl_per_s_per_gpu": B * NLAY * NG_LW / (lw_ms * 1e-3), "sw_gptl_per_s_per_gpu": B * NLAY * NG_SW / (sw_ms * 1e-3)},
         }

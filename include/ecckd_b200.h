@@ -137,6 +137,10 @@ int ecckd_get_ngpt(const ecckd_model *model);
 int ecckd_get_nband(const ecckd_model *model);
 int ecckd_get_band2gpt(const ecckd_model *model, int32_t *band2gpt /* (2,nband) */);
 int ecckd_get_band_lims_wvn(const ecckd_model *model, double *band_lims /* (2,nband) */);
+/* Loader hardening: the algorithm takes every grid spacing from the first two entries (gas_optics_ecckd.f90:104-106,
+ * 154-155,271) and so does this library; grids that are NOT uniform within 1e-3 are named in this string ("" = all
+ * uniform).  With ECCKD_STRICT_GRIDS=1 in the environment ecckd_model_create refuses such tables instead. */
+const char *ecckd_get_table_warnings(const ecckd_model *model);
 int ecckd_get_ndev(const ecckd_model *model);
 int ecckd_get_device(const ecckd_model *model, int dev_index);
 int ecckd_source_is_internal(const ecckd_model *model);

@@ -86,6 +86,7 @@ struct ecckd_model {
     std::vector<int32_t> band2gpt;
     double total_solar = 0.0;
     bool tables_nonneg = true, fp32_exact = true;
+    std::string warnings;       // grids that are not uniform although the algorithm assumes so (see ecckd_get_table_warnings)
     std::vector<std::unique_ptr<DevState>> devs;
 
     ~ecckd_model()
@@ -473,6 +474,42 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         M->total_solar = s;
     }
 
+    // ---- loader hardening ---------------------------------------------------
+    // The reference derives every grid spacing from the first two entries and silently assumes the grid is uniform
+    // (gas_optics_ecckd.f90:104-106,154-155,271).  The same is done here -- results must match the reference -- but
+    // tables that break the assumption are flagged (ecckd_get_table_warnings) or, with ECCKD_STRICT_GRIDS=1, refused.
+    {
+        const double tol = 1e-3;
+        auto nonuniform = [&](const double *x, int n, int stride) {
+            if (n < 3) return false;
+            const double d0 = x[stride] - x[0];
+            for (int i = 2; i < n; ++i)
+                if (std::fabs((x[(size_t)i * stride] - x[(size_t)(i - 1) * stride]) - d0) > tol * std::fabs(d0)) return true;
+            return false;
+        };
+        if (nonuniform(t->log_pressure, t->npress, 1)) M->warnings += "log_pressure is not uniformly spaced (:104-105); ";
+        bool tbad = false;
+        for (int ip = 0; ip < t->npress && !tbad; ++ip) tbad = nonuniform(t->temperature + ip, t->ntemp, t->npress);
+        const double dt0 = t->temperature[t->npress] - t->temperature[0];
+        for (int ip = 1; ip < t->npress && !tbad; ++ip)
+            tbad = std::fabs((t->temperature[t->npress + ip] - t->temperature[ip]) - dt0) > tol * std::fabs(dt0);
+        if (tbad) M->warnings += "temperature(p,:) is not a uniform grid with one spacing for all pressures (:106,131-133); ";
+        if (!t->shortwave && nonuniform(t->temperature_planck, t->nplanck, 1)) M->warnings += "temperature_planck is not uniformly spaced (:271); ";
+        for (int i = 0; i < t->num_gases; ++i) {
+            const ecckd_gas_table &g = t->gas[i];
+            if (g.concentration_dependence_code != ECCKD_CODE_LOOK_UP_TABLE || g.n_mole_fraction < 3 || !g.mole_fraction) continue;
+            std::vector<double> lg(g.n_mole_fraction);
+            bool pos = true;
+            for (int q = 0; q < g.n_mole_fraction; ++q) { pos = pos && g.mole_fraction[q] > 0.0; lg[q] = std::log(g.mole_fraction[q]); }
+            if (!pos || nonuniform(lg.data(), g.n_mole_fraction, 1))
+                M->warnings += "mole_fraction of " + trim_name(g.name, ECCKD_NAME_LEN) + " is not uniform in log space (:154-155); ";
+        }
+        if (!M->warnings.empty() && getenv("ECCKD_STRICT_GRIDS")) {
+            set_err(err, "ecckd_model_create: " + M->warnings);
+            return ECCKD_ERR_ARG;
+        }
+    }
+
     // pack all coefficient tables into one array; composite aliases share one copy
     std::vector<double> k64;
     const size_t slab = (size_t)t->ngpt * t->npress * t->ntemp;
@@ -699,6 +736,7 @@ int ecckd_get_band_lims_wvn(const ecckd_model *m, double *b)
     std::copy(m->band_lims.begin(), m->band_lims.end(), b);
     return ECCKD_OK;
 }
+const char *ecckd_get_table_warnings(const ecckd_model *m) { return m ? m->warnings.c_str() : ""; }
 int ecckd_get_ndev(const ecckd_model *m) { return m ? (int)m->devs.size() : 0; }
 int ecckd_get_device(const ecckd_model *m, int i) { return (m && i >= 0 && i < (int)m->devs.size()) ? m->devs[i]->device : -1; }
 int ecckd_source_is_internal(const ecckd_model *m) { return m && !m->shortwave; }                      // :487-493

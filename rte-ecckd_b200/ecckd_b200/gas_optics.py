@@ -305,6 +305,10 @@ class GasOpticsEcckd:
         self._lib.ecckd_get_band_lims_wvn(self._h, b.ctypes.data)
         return b
 
+    def get_table_warnings(self) -> str:
+        """Grids that are not uniform although the algorithm assumes so ("" when all are)."""
+        return self._lib.ecckd_get_table_warnings(self._h).decode()
+
     def get_ndev(self) -> int:
         return self._lib.ecckd_get_ndev(self._h)
 

@@ -25,7 +25,7 @@
 !! the kind of wp at compile time.
 !!
 !! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler.  INTEGRATION.md
-!! gives the build line and oracle/ref/stubs the modules it compiles against; tests/c/shim_sequence.c
+!! gives the build line (and names the stub rte-rrtmgp modules it can be compiled against); tests/c/shim_sequence.c
 !! replays this file's call sequence (model create from host tables with nband = 0 and blank-padded
 !! names, host entry points on pageable memory, error strings) in plain C on the GPU.
 module gas_optics_ecckd
