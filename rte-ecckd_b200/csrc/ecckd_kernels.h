@@ -39,6 +39,7 @@ void walk_plan(int ntile, bool shortwave, int sms, int &tiles_per_chunk, int &bl
 // quad kernel (ecckd_quad.cu): the product path for calls whose outputs admit TMA tensor maps
 constexpr int kQuadTileCols = 32;   // columns per tile
 constexpr int kQuadMaxVar = 3;      // bilinear gases with a varying concentration it keeps in registers
+constexpr int kQuadMaxExtra = 4;    // further varying gases it reads uncached (3 cached + 4: nvar <= 7)
 template <typename Real> bool quad_eligible(const CallGases &, const KernelArgs<Real> &);
 template <typename Real, bool SW>
 cudaError_t launch_quad(const DevModel &, const CallGases &, const KernelArgs<Real> &, const Real *mix, int sms, cudaStream_t);

@@ -52,11 +52,11 @@ constexpr int kNegFlag = 0x10000;       // key.x: upside-down layer whose negati
 
 // One layer of the record ring: structure-of-arrays over the 32 columns of the tile, so that the index warps
 // (lanes = columns) write and the compute warps (4 columns per warp) read without bank conflicts.
-template <typename Real, int NV> struct alignas(16) QRec {
+template <typename Real, int NV, int NX = 0> struct alignas(16) QRec {
     using P = typename PairOf<Real>::type;
     P c01[kQCols], c23[kQCols];   // tw0*pw0, tw0*pw1 | tw1*pw0, tw1*pw1
     P lut[kQCols];                // LUT gas: weight (0 when it does not contribute), vmr_weight1
-    P w[(NV + 2) / 2][kQCols];    // weights: mixed table, varying gases 1..NV (0 when clamped away)
+    P w[(NV + NX + 2) / 2][kQCols];   // weights: mixed table, varying gases 1..NV+NX (0 when clamped away)
     P aux[kQCols];                // simple_weight (SW: moles_per_layer; upside-down layers), unused
     int2 key[kQCols];             // x: bilinear corner offset | kNegFlag; y: LUT corner offset
 };
@@ -113,6 +113,18 @@ __device__ __forceinline__ int2 lds_int2(unsigned addr)
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+// fp32 -> fp64 on the integer pipe (exact for zero and normal numbers, which is what the Planck table holds: checked at
+// model create).  F2F runs on the 16-lane conversion unit that the compute warps' table rows also need; three ALU
+// operations and a select are cheaper there than one more F2F on the critical unit.
+template <typename Real> __device__ __forceinline__ Real widen_(float f, bool alu);
+template <> __device__ __forceinline__ float widen_<float>(float f, bool) { return f; }
+template <> __device__ __forceinline__ double widen_<double>(float f, bool alu)
+{
+    if (!alu) return (double)f;
+    const unsigned b = __float_as_uint(f);
+    const unsigned hi = b ? (b >> 3) + 0x38000000u : 0u;      // rebias 127 -> 1023: (e + 896) << 20; the sign bit is zero here
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
 template <typename Real> __device__ __forceinline__ void sts_(unsigned addr, Real v);
 template <> __device__ __forceinline__ void sts_<double>(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
@@ -121,17 +133,20 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 
 // Real   double | float (arithmetic and I/O type; index arithmetic is always double)
 // NV     register-cached varying bilinear gases (1 or 3); the call's nvar may be smaller
+// NX     further varying gases (0 or 6) whose corner rows are NOT cached: four 16-byte loads per gas and layer, used once
+//        (host models that pass co2 / ch4 / n2o / cfc11 / cfc12 as profiles or fields instead of scalars)
 // LUT32  cache the look-up-table rows as fp32 (exact: the files are f4) and widen them in the FMA chain
 // R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
 // L      positions (layers) per hand-off: record slots and staging tiles change hands in groups of L, so that the
 //        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
 {
-    using RecT = QRec<Real, NV>;
+    using RecT = QRec<Real, NV, NX>;
+    constexpr int NW2 = (NV + NX + 2) / 2;                 // weight pairs of a record
     using P = typename PairOf<Real>::type;
     using LutT = typename std::conditional<LUT32, float, Real>::type;
     constexpr int NOUT = SW ? 2 : 1;                       // staged outputs: tau (+ ssa)
@@ -247,6 +262,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             if (ECCKD_DBG(64)) return;
             const int S_ = m.nplanck;
             const bool has_lev = a.tlev != nullptr;
+            const bool alu_cvt = m.planck_alu_widen != 0 && !ECCKD_DBG(1024);
             const int nlevu = has_lev ? nlay + 1 : nlay;          // levels 0..nlay carry a value when tlev is present
             const int nunit = nslot * nlevu;
             auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
@@ -299,8 +315,8 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         Real vl[GB], vv[GB];
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
-                            vl[k] = fma_(l1, (Real)pl[k].y, mul_(l0, (Real)pl[k].x));
-                            vv[k] = fma_(v1, (Real)pv[k].y, mul_(v0, (Real)pv[k].x));      // B(tlev(:,j))
+                            vl[k] = fma_(l1, widen_<Real>(pl[k].y, alu_cvt), mul_(l0, widen_<Real>(pl[k].x, alu_cvt)));
+                            vv[k] = fma_(v1, widen_<Real>(pv[k].y, alu_cvt), mul_(v0, widen_<Real>(pv[k].x, alu_cvt)));      // B(tlev(:,j))
                         }
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
@@ -318,7 +334,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         for (int k = 0; k < GB; ++k) pl[k] = tl_p[min(gq + k, ng - 1) * S_];
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
-                            const Real vl = fma_(l1, (Real)pl[k].y, mul_(l0, (Real)pl[k].x));
+                            const Real vl = fma_(l1, widen_<Real>(pl[k].y, alu_cvt), mul_(l0, widen_<Real>(pl[k].x, alu_cvt)));
                             stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && gq + k < ng);
                             p_lay += plane_b;
                         }
@@ -354,7 +370,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         int slot = iw % R, n = iw / R;                          // ring slot of s and how often it has been used before
         // The inputs of a position stream in from DRAM (latency of microseconds under the kernel's write load): they are
         // fetched one position ahead of the arithmetic, like the Planck warps do.
-        struct In { double pu, pl, tl, vl, vv[NV]; };
+        struct In { double pu, pl, tl, vl, vv[NV + NX]; };
         auto fetch = [&](int ts_, int j_, In &in) {
             const long long col = min((long long)((int)blockIdx.x + ts_ * (int)gridDim.x) * kQCols + lane, (long long)ncol - 1);
             // (tail tiles recompute the last column; never stored)
@@ -363,8 +379,23 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             in.tl = (double)a.tlay[col + (long long)ncol * j_];
             in.vl = has_lut ? load_vmr<Real>(cg.g[cg.lut], col, j_) : 0.0;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) in.vv[v] = v < nvar ? load_vmr<Real>(cg.g[cg.var_gas[v]], col, j_) : 0.0;
+            for (int v = 0; v < NV + NX; ++v) in.vv[v] = v < nvar ? load_vmr<Real>(cg.g[cg.var_gas[v]], col, j_) : 0.0;
         };
+        // ... and pulled into L2 kPF positions of this warp earlier still (no registers: prefetch.global.L2), so that the
+        // register fetch one position ahead finds them a few hundred cycles away instead of a DRAM round trip
+        constexpr int kPF = 4;
+        auto prefetch = [&](int ts_, int j_) {
+            const long long col = min((long long)((int)blockIdx.x + ts_ * (int)gridDim.x) * kQCols + lane, (long long)ncol - 1);
+            auto pf = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+            pf(a.plev + col + (long long)ncol * (j_ + 1));
+            pf(a.tlay + col + (long long)ncol * j_);
+            if (has_lut) { const GasRef &gr = cg.g[cg.lut]; pf(static_cast<const Real *>(gr.vmr) + col * gr.col_stride + (long long)j_ * gr.lay_stride); }
+#pragma unroll
+            for (int v = 0; v < NV + NX; ++v)
+                if (v < nvar) { const GasRef &gr = cg.g[cg.var_gas[v]]; pf(static_cast<const Real *>(gr.vmr) + col * gr.col_stride + (long long)j_ * gr.lay_stride); }
+        };
+        int pj = j, pts = ts;                                   // position kPF * kQNI ahead of s
+        for (int q2 = 0; q2 < kPF; ++q2) { pj += kQNI; while (pj >= nlay) { pj -= nlay; ++pts; } }
         In nxt;
         if (iw < S) fetch(ts, j, nxt);
         for (int s = iw; s < Spad; s += kQNI) {
@@ -373,13 +404,15 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 int j2 = j + kQNI, ts2 = ts;
                 while (j2 >= nlay) { j2 -= nlay; ++ts2; }
                 if (s + kQNI < S) fetch(ts2, j2, nxt);
+                if (!ECCKD_DBG(512) && s + kPF * kQNI < S) prefetch(pts, pj);
+                pj += kQNI; while (pj >= nlay) { pj -= nlay; ++pts; }
             }
-            P c01, c23, lutw, wv[(NV + 2) / 2], aux;
+            P c01, c23, lutw, wv[NW2], aux;
             int2 key;
             if ((ECCKD_DBG(2) && s >= R) || s >= S) {   // (s >= S: padding position of the last hand-off group, never stored)
                 c01 = c23 = lutw = aux = make_pair_<P>(0.25, 0.25); key = make_int2(0, 0);
 #pragma unroll
-                for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = c01;
+                for (int v = 0; v < NW2; ++v) wv[v] = c01;
             } else {
                 const CellIndex ci = cell_index(m, in.pu, in.pl, in.tl);
                 const double pw0 = __dsub_rn(1.0, ci.pw1), tw0 = __dsub_rn(1.0, ci.tw1);
@@ -390,10 +423,10 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 // becomes "the gas contributes nothing when its weight is negative" -- its weight is stored as 0,
                 // which leaves tau unchanged bit for bit (fma(0, finite, tau) == tau); NaN weights propagate.
                 const bool up = ci.sw < 0.0;
-                double W[NV + 1];
+                double W[NV + NX + 1];
                 W[0] = (has_mix && !up) ? ci.sw : 0.0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
+                for (int v = 0; v < NV + NX; ++v) {
                     double wd = 0.0;
                     if (v < nvar) {
                         wd = gas_weight(cg.g[cg.var_gas[v]], ci.sw, in.vv[v]);
@@ -402,7 +435,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     W[v + 1] = wd;
                 }
 #pragma unroll
-                for (int v = 0; v < (NV + 2) / 2; ++v) wv[v] = make_pair_<P>(W[2 * v], 2 * v + 1 <= NV ? W[2 * v + 1] : 0.0);
+                for (int v = 0; v < NW2; ++v) wv[v] = make_pair_<P>(W[2 * v], 2 * v + 1 <= NV + NX ? W[2 * v + 1] : 0.0);
                 aux = make_pair_<P>(ci.sw, 0.0);
                 key.x = (ip * kNTP + it) * kGP | ((has_mix && up) ? kNegFlag : 0);
                 key.y = 0;
@@ -421,7 +454,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             RecT &rc = recs[slot];
             rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane] = key;
 #pragma unroll
-            for (int v = 0; v < (NV + 2) / 2; ++v) rc.w[v][lane] = wv[v];
+            for (int v = 0; v < NW2; ++v) rc.w[v][lane] = wv[v];
             __syncwarp();
             if (lane == 0) mbar_arrive(&rec_full[slot / L]);
             j += kQNI; while (j >= nlay) { j -= nlay; ++ts; }
@@ -499,7 +532,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // record fields of this lane's column, as shared-window addresses relative to the ring slot
     constexpr unsigned PB = sizeof(P), RB = sizeof(RecT);
     constexpr unsigned O_C01 = 0, O_C23 = kQCols * PB, O_LUT = 2 * kQCols * PB, O_W = 3 * kQCols * PB,
-                       O_AUX = (3 + (NV + 2) / 2) * kQCols * PB, O_KEY = (4 + (NV + 2) / 2) * kQCols * PB;
+                       O_AUX = (3 + NW2) * kQCols * PB, O_KEY = (4 + NW2) * kQCols * PB;
     static_assert(O_KEY + kQCols * 8 == RB, "record layout");
     unsigned rec_a = smem_u32(recs) + ct * PB, key_a = smem_u32(recs) + O_KEY + ct * 8;
     // loop invariants are pinned in registers: otherwise they are rematerialised from kernel parameters and special
@@ -512,13 +545,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     if (S > 0) {
         // The record of a position is read into registers one position ahead, BEFORE the cache refill is issued: the
         // LSU queue is in order, so a record load behind 28 refill loads would wait for all of them.
-        struct Cur { P c01, c23, lw, wv[(NV + 2) / 2]; Real swt; int2 key; } cur;
+        struct Cur { P c01, c23, lw, wv[NW2]; Real swt; int2 key; } cur;
         auto load_rec = [&](int slot_) {
             const unsigned ra = rec_a + slot_ * RB;
             cur.key = lds_int2(key_a + slot_ * RB);
             cur.c01 = lds_pair<P>(ra + O_C01); cur.c23 = lds_pair<P>(ra + O_C23); cur.lw = lds_pair<P>(ra + O_LUT);
 #pragma unroll
-            for (int v = 0; v < (NV + 2) / 2; ++v) cur.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
+            for (int v = 0; v < NW2; ++v) cur.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
             cur.swt = SW ? lds_pair<P>(ra + O_AUX).x : (Real)0;
         };
         mbar_wait_a(a_rfull, 0);
@@ -549,6 +582,32 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     t = fma_(wgt, bv, t);
                 }
                 tau[i] = t;
+            }
+            if constexpr (NX > 0) {
+                // gases beyond the cached ones: corner rows straight from L1/L2, two gases in flight at a time
+                const float *xb = wbil + (cur.key.x & 0xffff);
+                auto rows_of = [&](int x, float4 (&r)[4]) {
+                    const bool on = NV + x < nvar;
+                    const float4 *p = reinterpret_cast<const float4 *>(xb + (on ? cg.var_off[NV + x] : 0));
+                    r[0] = __ldg(p + kC00 / 4); r[1] = __ldg(p + kC10 / 4); r[2] = __ldg(p + kC01 / 4); r[3] = __ldg(p + kC11 / 4);
+                };
+                auto acc = [&](int x, const float4 (&r)[4]) {
+                    const int wi = NV + x + 1;
+                    const Real wgt = (wi & 1) ? cur.wv[wi >> 1].y : cur.wv[wi >> 1].x;      // 0 for absent / clamped gases
+                    tau[0] = fma_(wgt, bil4(c0, c1, c2, c3, r[0].x, r[1].x, r[2].x, r[3].x), tau[0]);
+                    tau[1] = fma_(wgt, bil4(c0, c1, c2, c3, r[0].y, r[1].y, r[2].y, r[3].y), tau[1]);
+                    tau[2] = fma_(wgt, bil4(c0, c1, c2, c3, r[0].z, r[1].z, r[2].z, r[3].z), tau[2]);
+                    tau[3] = fma_(wgt, bil4(c0, c1, c2, c3, r[0].w, r[1].w, r[2].w, r[3].w), tau[3]);
+                };
+                float4 ra_[4], rb_[4];
+                rows_of(0, ra_);
+#pragma unroll
+                for (int x = 0; x < NX; x += 2) {
+                    rows_of(x + 1, rb_);
+                    acc(x, ra_);
+                    if (x + 2 < NX) rows_of(x + 2, ra_);
+                    acc(x + 1, rb_);
+                }
             }
             if (cur.key.x & kNegFlag) {   // upside-down layer: the negative-factor gases give positive optical depth
                 const Real *k = wmix + (size_t)ngroups * kSlab + (cur.key.x & 0xffff);
@@ -620,13 +679,13 @@ template <typename Real> static bool encode_quad_map(CUtensorMap *map, Real *ptr
 
 template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArgs<Real> &a)
 {
-    if (cg.nvar > kQuadMaxVar) return false;
+    if (cg.nvar > kQuadMaxVar + kQuadMaxExtra) return false;
     if ((size_t)a.ncol * sizeof(Real) % 16) return false;            // tensor-map strides are multiples of 16 bytes
     for (int o = 0; o < 3; ++o) if (a.out[o] && (reinterpret_cast<uintptr_t>(a.out[o]) & 15)) return false;
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -634,9 +693,9 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
     TmaMaps maps{};
     for (int o = 0; o < (SW ? 3 : 1); ++o)
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV>) * R +
+    const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
                         (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L>;
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
@@ -667,6 +726,15 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         if (v == 7) return launch_quad_t<Real, SW, 1, true, 8, 4, 152, 96, 112>(m, cg, a, mix, sms, s);
         if (v == 8) return launch_quad_t<Real, SW, 1, true, 32, 8, 152, 96, 112>(m, cg, a, mix, sms, s);
         if (v == 9) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88>(m, cg, a, mix, sms, s);
+        if (v == 41) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96>(m, cg, a, mix, sms, s);
+        if (v == 42) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 64, 112>(m, cg, a, mix, sms, s);
+        if (v == 43) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 72, 104>(m, cg, a, mix, sms, s);
+        if (v == 44) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 64, 96>(m, cg, a, mix, sms, s);
+        if (v == 45) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88>(m, cg, a, mix, sms, s);
+        if (v == 46) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 80>(m, cg, a, mix, sms, s);
+        if (v == 47) return launch_quad_t<Real, SW, 1, false, 8, 4, 168, 80, 96>(m, cg, a, mix, sms, s);
+        if (v == 48) return launch_quad_t<Real, SW, 1, true, 16, 6, 160, 64, 128>(m, cg, a, mix, sms, s);
+        if (v == 49) return launch_quad_t<Real, SW, 1, true, 16, 6, 144, 96, 128>(m, cg, a, mix, sms, s);
         if (v == 21) return launch_quad_t<Real, SW, 1, true, 16, 3, 152, 80, 128, false, 2>(m, cg, a, mix, sms, s);
         if (v == 22) return launch_quad_t<Real, SW, 1, true, 16, 2, 152, 80, 128, false, 4>(m, cg, a, mix, sms, s);
         if (v == 23) return launch_quad_t<Real, SW, 1, false, 16, 3, 184, 64, 64, true, 2>(m, cg, a, mix, sms, s);
@@ -689,10 +757,15 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     //                                          NV  LUT32   R NBUF   RC   RI   RH  ZERO_BY_TMA
     if (cg.nvar <= 1) {
         if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
-        else return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false>(m, cg, a, mix, sms, s);
     }
-    if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
-    else return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 176, 72, 88, false>(m, cg, a, mix, sms, s);
+    if (cg.nvar <= kQuadMaxVar) {      // up to three varying gases, all cached (fp32 LUT rows to make room)
+        if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 176, 72, 88, false>(m, cg, a, mix, sms, s);
+    }
+    // four to seven varying gases: three cached, the others read uncached every layer
+    if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 8, 6, 184, 96, 48, true, 1, kQuadMaxExtra>(m, cg, a, mix, sms, s);
+    else return launch_quad_t<Real, SW, kQuadMaxVar, true, 8, 6, 176, 80, 80, false, 1, kQuadMaxExtra>(m, cg, a, mix, sms, s);
 }
 
 #define ECCKD_QUAD_INST(Real)                                                                                                   \

@@ -58,6 +58,8 @@ _SIGS = {
     "ecckd_get_band2gpt": (_i, [_vp, _vp]),
     "ecckd_get_band_lims_wvn": (_i, [_vp, _vp]),
     "ecckd_get_table_warnings": (C.c_char_p, [_vp]),
+    "ecckd_host_register": (_i, [_vp, C.c_size_t, _cp]),
+    "ecckd_host_unregister": (_i, [_vp]),
     "ecckd_get_ndev": (_i, [_vp]),
     "ecckd_get_device": (_i, [_vp, _i]),
     "ecckd_source_is_internal": (_i, [_vp]),
