@@ -139,8 +139,9 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 // R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
 // L      positions (layers) per hand-off: record slots and staging tiles change hands in groups of L, so that the
 //        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
+// EARLYREC  read the record of the next position at the top of the iteration (ahead of the arithmetic) instead of after it
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -543,28 +544,38 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     for (int v = 0; v < NV; ++v) keep(wvar[v]);
 
     if (S > 0) {
-        // The record of a position is read into registers one position ahead, BEFORE the cache refill is issued: the
-        // LSU queue is in order, so a record load behind 28 refill loads would wait for all of them.
-        struct Cur { P c01, c23, lw, wv[NW2]; Real swt; int2 key; } cur;
-        auto load_rec = [&](int slot_) {
+        // The record of position s + 1 is read into registers one position ahead.  EARLYREC reads it at the TOP of
+        // iteration s, ahead of the arithmetic of s (the LSU queue is in order: record loads issued behind the 28 refill
+        // loads wait for all of them, 10 % of the compute warps' stall samples) -- but the 20 extra live registers spill,
+        // and that costs more (measured: SW 1.88 -> 2.24 ms, LW 2.17 -> 2.48 ms), so the default reads it after the arithmetic.
+        struct Cur { P c01, c23, lw, wv[NW2]; Real swt; int2 key; };
+        auto load_rec = [&](int slot_, Cur &r) {
             const unsigned ra = rec_a + slot_ * RB;
-            cur.key = lds_int2(key_a + slot_ * RB);
-            cur.c01 = lds_pair<P>(ra + O_C01); cur.c23 = lds_pair<P>(ra + O_C23); cur.lw = lds_pair<P>(ra + O_LUT);
+            r.key = lds_int2(key_a + slot_ * RB);
+            r.c01 = lds_pair<P>(ra + O_C01); r.c23 = lds_pair<P>(ra + O_C23); r.lw = lds_pair<P>(ra + O_LUT);
 #pragma unroll
-            for (int v = 0; v < NW2; ++v) cur.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
-            cur.swt = SW ? lds_pair<P>(ra + O_AUX).x : (Real)0;
+            for (int v = 0; v < NW2; ++v) r.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
+            r.swt = SW ? lds_pair<P>(ra + O_AUX).x : (Real)0;
         };
+        Cur cur, nxt;
         mbar_wait_a(a_rfull, 0);
-        load_rec(0);
+        load_rec(0, cur);
         refill(cur.key.x & 0xffff, cur.key.y);
+        nxt = cur;
         int slot = 0, rpar = 0, b = 0, tpar = 1;       // tpar: parity to wait for on tile_empty (the phase before the
                                                        // initial one counts as complete, so the first pass never blocks)
+        int lane0 = lane == 0;
+        keep(lane0);
         int ls = 0;                                    // position inside the hand-off group
         for (int s = 0; s < Spad; ++s) {
+            const int nslot_r = slot + 1 == R ? 0 : slot + 1;
+            if (EARLYREC && s + 1 < Spad) {
+                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
+                load_rec(nslot_r, nxt);
+            }
             const Real c0 = cur.c01.x, c1 = cur.c01.y, c2 = cur.c23.x, c3 = cur.c23.y;
             const Real omv = add_((Real)1, -cur.lw.y);
             Real tau[4];
-            const int nslot_r = slot + 1 == R ? 0 : slot + 1;
             if (ECCKD_DBG(4)) { tau[0] = c0; tau[1] = c1; tau[2] = c2; tau[3] = c3; }
             else
 #pragma unroll
@@ -619,13 +630,12 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 }
             }
             const Real swt = cur.swt;
-            // the cache and the record have been read: fetch the next position's record, then its corners, under the
-            // rest of this layer's work
-            if (s + 1 < Spad) {
-                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
-                load_rec(nslot_r);
-                refill(cur.key.x & 0xffff, cur.key.y);
+            // the cache has been read: fetch the next position's corners under the rest of this layer's work
+            if (!EARLYREC && s + 1 < Spad) {     // (the other order: record loads right in front of the refill loads)
+                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
+                load_rec(nslot_r, nxt);
             }
+            if (s + 1 < Spad) refill(nxt.key.x & 0xffff, nxt.key.y);
             Real ssa[4];
             if (SW) {
 #pragma unroll
@@ -648,12 +658,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 ls = 0;
                 if (!ECCKD_DBG(16)) fence_proxy_async_smem();      // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
-                if (lane == 0) {
+                if (lane0) {
                     mbar_arrive_a(a_tfull + b * 8);
                     mbar_arrive_a(a_rempty + (slot / L) * 8);
                 }
                 if (++b == NBUF) { b = 0; tpar ^= 1; }
             }
+            cur = nxt;
             slot = nslot_r;
             if (slot == 0) rpar ^= 1;
         }
@@ -685,7 +696,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -695,7 +706,7 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
                         (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX>;
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
@@ -716,37 +727,17 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
-        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA
-        if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
-        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 80>(m, cg, a, mix, sms, s);
-        if (v == 3) return launch_quad_t<Real, SW, 1, true, 16, 6, 184, 64, 64>(m, cg, a, mix, sms, s);
-        if (v == 4) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 96, 112>(m, cg, a, mix, sms, s);
-        if (v == 5) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 112, 96>(m, cg, a, mix, sms, s);
-        if (v == 6) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128>(m, cg, a, mix, sms, s);
-        if (v == 7) return launch_quad_t<Real, SW, 1, true, 8, 4, 152, 96, 112>(m, cg, a, mix, sms, s);
-        if (v == 8) return launch_quad_t<Real, SW, 1, true, 32, 8, 152, 96, 112>(m, cg, a, mix, sms, s);
-        if (v == 9) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88>(m, cg, a, mix, sms, s);
-        if (v == 41) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96>(m, cg, a, mix, sms, s);
-        if (v == 42) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 64, 112>(m, cg, a, mix, sms, s);
-        if (v == 43) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 72, 104>(m, cg, a, mix, sms, s);
-        if (v == 44) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 64, 96>(m, cg, a, mix, sms, s);
-        if (v == 45) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88>(m, cg, a, mix, sms, s);
-        if (v == 46) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 80>(m, cg, a, mix, sms, s);
-        if (v == 47) return launch_quad_t<Real, SW, 1, false, 8, 4, 168, 80, 96>(m, cg, a, mix, sms, s);
-        if (v == 48) return launch_quad_t<Real, SW, 1, true, 16, 6, 160, 64, 128>(m, cg, a, mix, sms, s);
-        if (v == 49) return launch_quad_t<Real, SW, 1, true, 16, 6, 144, 96, 128>(m, cg, a, mix, sms, s);
-        if (v == 21) return launch_quad_t<Real, SW, 1, true, 16, 3, 152, 80, 128, false, 2>(m, cg, a, mix, sms, s);
-        if (v == 22) return launch_quad_t<Real, SW, 1, true, 16, 2, 152, 80, 128, false, 4>(m, cg, a, mix, sms, s);
-        if (v == 23) return launch_quad_t<Real, SW, 1, false, 16, 3, 184, 64, 64, true, 2>(m, cg, a, mix, sms, s);
-        if (v == 24) return launch_quad_t<Real, SW, 1, false, 16, 2, 184, 64, 64, true, 4>(m, cg, a, mix, sms, s);
-        if (v == 25) return launch_quad_t<Real, SW, 1, false, 16, 3, 168, 80, 80, false, 2>(m, cg, a, mix, sms, s);
-        if (v == 26) return launch_quad_t<Real, SW, 1, false, 16, 2, 168, 80, 80, false, 4>(m, cg, a, mix, sms, s);
-        if (v == 27) return launch_quad_t<Real, SW, 1, true, 32, 4, 152, 80, 128, false, 4>(m, cg, a, mix, sms, s);
-        if (v == 28) return launch_quad_t<Real, SW, 1, false, 32, 4, 184, 64, 64, true, 4>(m, cg, a, mix, sms, s);
-        if (v == 11) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 96, 32, true>(m, cg, a, mix, sms, s);
-        if (v == 12) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 128, 80, true>(m, cg, a, mix, sms, s);
-        if (v == 13) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 88, 40, true>(m, cg, a, mix, sms, s);
-        if (v == 10) return launch_quad_t<Real, SW, 1, true, 16, 6, 160, 104, 88>(m, cg, a, mix, sms, s);
+        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC
+        if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false>(m, cg, a, mix, sms, s);
+        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false>(m, cg, a, mix, sms, s);
+        if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 5) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88, false, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, false, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 7) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 72, 72, true, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 8) return launch_quad_t<Real, SW, 1, false, 16, 6, 192, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 9) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false, 1, 0, true>(m, cg, a, mix, sms, s);
+        if (v == 10) return launch_quad_t<Real, SW, 1, false, 16, 3, 176, 64, 96, false, 2, 0, false>(m, cg, a, mix, sms, s);
     }
 #endif
     // Production instantiations, as measured on B200 (tools/exp_quad.sh):
