@@ -240,6 +240,11 @@ int ecckd_interpolation_indices_f64(ecckd_model *model, int dev_index, int ncol,
 int ecckd_planck_indices_f64(ecckd_model *model, int dev_index, int64_t n, const double *temperature,
                              int32_t *it0, double *w1, void *stream, char err[ECCKD_ERRLEN]);
 
+/* debug: the kernels divide by per-model constants (grid spacings, pi) with a reciprocal multiplication plus an exact FMA
+ * residual correction (correctly rounded: bit for bit the IEEE quotient the reference computes).  This runs that
+ * sequence next to the device's IEEE division on `n` dividends in device memory and counts the quotients that differ. */
+int ecckd_debug_div_const(int64_t n, const double *x_dev, double divisor, uint64_t *mismatches, char err[ECCKD_ERRLEN]);
+
 /* debug: launch geometry of the column-walking kernel for a call of `ncol` columns on a device with `sm_count` SMs --
  * 16-column tiles are grouped into chunks of `tiles_per_chunk` (1 or 2) and block b of `blocks` walks chunks
  * b, b + blocks, ...  Host arithmetic only (no device needed); the CPU tests check that every tile is walked once. */

@@ -47,6 +47,17 @@ struct NvtxRange {
     ~NvtxRange() { nvtxRangePop(); }
 };
 
+// RN(1/c) for div_const (ecckd_device.cuh), or NaN when the Markstein argument does not cover c: zero / non-finite
+// divisors and significands that are all ones.
+double const_reciprocal(double c)
+{
+    unsigned long long b;
+    std::memcpy(&b, &c, 8);
+    if (!(std::fabs(c) > 0.0) || !std::isfinite(c) || (b & 0xfffffffffffffull) == 0xfffffffffffffull) return std::nan("");
+    const double r = 1.0 / c;
+    return (std::isfinite(r) && std::fabs(r) > 2.3e-308) ? r : std::nan("");
+}
+
 void set_err(char *err, const std::string &msg)
 {
     if (!err) return;
@@ -142,6 +153,7 @@ int resolve_gases(const ecckd_model *M, int ngas, const char *const *names, cons
         g.ref = M->ref[i]; g.nv = M->nv[i];
         g.mf0 = M->mf0[i]; g.log_mf0 = M->log_mf0[i]; g.dlog_mf = M->dlog_mf[i];
         g.v_clamp = (double)M->nv[i] - 1.001;                                          // :160
+        g.r_dlog_mf = const_reciprocal(g.dlog_mf);
         if (g.code == kLut) { if (nlut++ == 0) cg.lut = cg.n; }
         else {
             ++cg.nbil;
@@ -548,10 +560,12 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
     }
     if (k64.size() >= (size_t)1 << 30) { set_err(err, "ecckd_model_create: tables too large"); return ECCKD_ERR_ARG; }
     std::vector<float> k32(k64.size());
+    bool fp32_normal = true;    // no fp32 subnormals: the walking kernels may widen table rows with integer operations
     for (size_t q = 0; q < k64.size(); ++q) {
         k32[q] = (float)k64[q];
         if ((double)k32[q] != k64[q]) M->fp32_exact = false;
         if (k64[q] < 0.0) M->tables_nonneg = false;
+        if (k32[q] != 0.0f && std::fabs(k32[q]) < 1.17549435e-38f) fp32_normal = false;
     }
     std::vector<double> p64;
     std::vector<float> p32;
@@ -576,7 +590,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
             if (sidx < 0) { sidx = nslot++; slot_off.push_back(M->table_off[i]); }
             M->slot[i] = sidx;
         }
-        M->walk_model = M->tables_nonneg && M->fp32_exact && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP &&
+        M->walk_model = M->tables_nonneg && M->fp32_exact && fp32_normal && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP &&
                         M->nplanck <= 256;   // the per-block shared-memory copy of the Planck LUT must fit beside records and tiles
         if (M->walk_model) {
             const int ngroups = (t->ngpt + kGP - 1) / kGP, ng = t->ngpt, np = t->npress, nt = t->ntemp;
@@ -648,6 +662,9 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         dm.t_clamp = (double)t->ntemp - 1.0001;
         dm.pi = (double)3.14159265359f;                                                  // :53
         if (!t->shortwave) { dm.tp0 = t->temperature_planck[0]; dm.dtp = t->temperature_planck[1] - t->temperature_planck[0]; }
+        dm.r_dlogp = const_reciprocal(dm.dlogp); dm.r_dt = const_reciprocal(dm.dt); dm.r_pi = const_reciprocal(dm.pi);
+        dm.r_dtp = t->shortwave ? std::nan("") : const_reciprocal(dm.dtp);
+        dm.r_tp0 = t->shortwave ? std::nan("") : const_reciprocal(dm.tp0);
         int rc;
         M->devs.push_back(std::move(ds));
         DevState &d2 = *M->devs.back();
@@ -851,6 +868,7 @@ int ecckd_interpolation_indices_f64(ecckd_model *M, int dev_index, int ncol, int
                 lut.vmr = lut_vmr->ptr; lut.col_stride = lut_vmr->col_stride; lut.lay_stride = lut_vmr->lay_stride;
                 lut.code = kLut; lut.nv = M->nv[q]; lut.mf0 = M->mf0[q]; lut.log_mf0 = M->log_mf0[q]; lut.dlog_mf = M->dlog_mf[q];
                 lut.v_clamp = (double)M->nv[q] - 1.001;
+                lut.r_dlog_mf = const_reciprocal(lut.dlog_mf);
                 has = true;
                 break;
             }
@@ -859,6 +877,22 @@ int ecckd_interpolation_indices_f64(ecckd_model *M, int dev_index, int ncol, int
     DevState &d = *M->devs[dev_index];
     CUDA_TRY(cudaSetDevice(d.device));
     CUDA_TRY(launch_indices<double>(d.dm, has ? &lut : nullptr, ncol, nlay, plev, tlay, ip0, pw1, it0, tw1, iv0, vw1, (cudaStream_t)stream));
+    return ECCKD_OK;
+}
+
+int ecckd_debug_div_const(int64_t n, const double *x_dev, double divisor, uint64_t *mismatches, char err[ECCKD_ERRLEN])
+{
+    if (err) err[0] = '\0';
+    if (n < 0 || !x_dev || !mismatches) { set_err(err, "ecckd_debug_div_const: bad argument"); return ECCKD_ERR_ARG; }
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
+    cudaError_t e = n > 0 ? launch_div_const_check(n, x_dev, divisor, const_reciprocal(divisor), d, nullptr) : cudaSuccess;
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_TRY(e);
+    *mismatches = h;
     return ECCKD_OK;
 }
 

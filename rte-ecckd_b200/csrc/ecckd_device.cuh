@@ -50,6 +50,8 @@ struct DevModel {
     double t_clamp;    // size(temperature,2) - 1.0001_wp              :137
     double tp0, dtp;   // temperature_planck(1), (2)-(1)               :271-272
     double pi;         // (double)3.14159265359f                       :53
+    // correctly rounded reciprocals of the constant divisors (NaN: divisor unsuitable, div_const falls back to __ddiv_rn)
+    double r_dlogp, r_dt, r_dtp, r_tp0, r_pi;
     const double *tbase;     // temperature(:,1)                       :131-132
     const float *k32;        // all coefficient tables, fp32 (exact)   element (g,p,t,v) of a gas at
     const double *k64;       //   off + g + ngpt*(p + np*(t + nt*v)), 0-based
@@ -75,6 +77,7 @@ struct GasRef {
     double mf0;                        // mole_fraction(1)                 :153
     double log_mf0;                    // log(mole_fraction(1))            :156
     double dlog_mf;                    // log(mole_fraction(2)/mole_fraction(1))  :154-155
+    double r_dlog_mf;                  // RN(1 / dlog_mf) for div_const
     double v_clamp;                    // size(mole_fraction) - 1.001_wp   :160
     int code;
     int nv;
@@ -111,6 +114,19 @@ template <> struct TableOf<float> {
     __device__ static const float *wlut(const DevModel &m) { return m.wlut32; }
 };
 
+// x / c for a divisor c that is constant over the call, given rc = RN(1/c):  q0 = RN(x*rc), r = x - c*q0 (exact in one
+// FMA), q = RN(q0 + r*rc).  With a correctly rounded reciprocal and q0 within an ulp of x/c this IS the correctly rounded
+// quotient (Markstein 1990; the one excluded case, a divisor whose significand is all ones, is detected on the host,
+// which then passes rc = NaN) -- bit for bit what __ddiv_rn and the reference's division return, in 3 dependent fp64
+// operations instead of ~25 instructions.  Non-finite dividends take q0 as it is (inf / c = inf, NaN stays NaN).
+__device__ __forceinline__ double div_const(double x, double c, double rc)
+{
+    if (rc != rc) return __ddiv_rn(x, c);                  // uniform over the launch
+    const double q0 = __dmul_rn(x, rc);
+    const double q = __fma_rn(__fma_rn(-c, q0, x), rc, q0);
+    return fabs(q0) < __longlong_as_double(0x7ff0000000000000ll) ? q : q0;
+}
+
 // ---- per-cell interpolation state (pressure, temperature) -------------------
 struct CellIndex {
     int ip0, it0;      // 1-based, as in the reference
@@ -123,13 +139,13 @@ __device__ __forceinline__ CellIndex cell_index(const DevModel &m, double p_uppe
     // p_upper = level_pressure(i,j), p_lower = level_pressure(i,j+1)
     CellIndex c;
     double lp = log(__dmul_rn(0.5, __dadd_rn(p_lower, p_upper)));                     // :120
-    double x = __ddiv_rn(__dsub_rn(lp, m.logp0), m.dlogp);                            // :121
+    double x = div_const(__dsub_rn(lp, m.logp0), m.dlogp, m.r_dlogp);                 // :121
     x = __dadd_rn(1.0, fmax(0.0, fmin(x, m.p_clamp)));                                // :122-125
     c.ip0 = __double2int_rz(x);                                                       // :126
     c.pw1 = __dsub_rn(x, (double)c.ip0);
     double pw0 = __dsub_rn(1.0, c.pw1);
     double t0 = __dadd_rn(__dmul_rn(pw0, m.tbase[c.ip0 - 1]), __dmul_rn(c.pw1, m.tbase[c.ip0]));  // :131-132
-    double y = __ddiv_rn(__dsub_rn(tlay, t0), m.dt);                                  // :133
+    double y = div_const(__dsub_rn(tlay, t0), m.dt, m.r_dt);                          // :133
     y = __dadd_rn(1.0, fmax(0.0, fmin(y, m.t_clamp)));                                // :134-137
     c.it0 = __double2int_rz(y);                                                       // :138
     c.tw1 = __dsub_rn(y, (double)c.it0);
@@ -149,7 +165,7 @@ __device__ __forceinline__ double gas_weight(const GasRef &g, double sw, double 
 __device__ __forceinline__ int vmr_index(const GasRef &g, double vmr, double &vw1)
 {
     double lv = log(fmax(vmr, g.mf0));                                                // :153
-    double z = __ddiv_rn(__dsub_rn(lv, g.log_mf0), g.dlog_mf);                        // :156
+    double z = div_const(__dsub_rn(lv, g.log_mf0), g.dlog_mf, g.r_dlog_mf);           // :156
     z = __dadd_rn(1.0, fmax(0.0, fmin(z, g.v_clamp)));                                // :157-160
     int iv0 = __double2int_rz(z);                                                     // :161
     vw1 = __dsub_rn(z, (double)iv0);
@@ -161,7 +177,7 @@ __device__ __forceinline__ int vmr_index(const GasRef &g, double vmr, double &vw
 // BEFORE the division by pi: in range (w0, w1); below range (T/t0, 0).
 __device__ __forceinline__ int planck_index(const DevModel &m, double T, double &a0, double &a1)
 {
-    double x = __ddiv_rn(__dsub_rn(T, m.tp0), m.dtp);                                 // :275
+    double x = div_const(__dsub_rn(T, m.tp0), m.dtp, m.r_dtp);                        // :275
     if (x >= 0.0) {
         x = __dadd_rn(1.0, x);                                                        // :277
         int it0 = min(__double2int_rz(x), m.nplanck - 1);                             // :278
@@ -169,7 +185,7 @@ __device__ __forceinline__ int planck_index(const DevModel &m, double T, double 
         a0 = __dsub_rn(1.0, a1);                                                      // :280
         return it0;
     }
-    a0 = __ddiv_rn(T, m.tp0);                                                         // :284
+    a0 = div_const(T, m.tp0, m.r_tp0);                                                // :284
     a1 = 0.0;
     return 0;
 }

@@ -448,13 +448,13 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             double a0, a1;
             int it = planck_index(m, tl, a0, a1);
             const float2 *tl_p = spl2 + (max(it, 1) - 1);
-            const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
+            const Real l0 = (Real)div_const(a0, m.pi, m.r_pi), l1 = (Real)div_const(a1, m.pi, m.r_pi);
             unsigned off = (unsigned)colp + (unsigned)ncol * (unsigned)j + plane32 * (unsigned)g0;
             int so = 0;
             if (has_lev) {
                 it = planck_index(m, tv, a0, a1);
                 const float2 *tv_p = spl2 + (max(it, 1) - 1);
-                const Real v0 = (Real)__ddiv_rn(a0, m.pi), v1 = (Real)__ddiv_rn(a1, m.pi);
+                const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
 #pragma unroll 4
                 for (int gq = 0; gq < ng; ++gq, off += plane32, so += S) {
                     const float2 pl = tl_p[so], pv = tv_p[so];
@@ -480,7 +480,7 @@ walk_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 double a0, a1;
                 const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
                 const int r = max(it, 1) - 1;
-                const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
+                const Real s0 = (Real)div_const(a0, m.pi, m.r_pi), s1 = (Real)div_const(a1, m.pi, m.r_pi);
                 for (int gq = lsel; gq < ng; gq += LPU)
                     if (cc < ncol) {
                         const float2 ps = spl2[gq * S + r];
@@ -800,6 +800,22 @@ __global__ void planck_indices_kernel(const __grid_constant__ DevModel m, long l
     double a0, a1;
     const int it = planck_index(m, T[idx], a0, a1);
     it0[idx] = it; w1[idx] = it > 0 ? a1 : 0.0;
+}
+
+// div_const against the IEEE division it replaces: number of dividends whose quotients differ in any bit
+__global__ void div_const_check_kernel(long long n, const double *x, double c, double rc, unsigned long long *mismatches)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double a = div_const(x[idx], c, rc), b = __ddiv_rn(x[idx], c);
+    const bool same = (a != a && b != b) || __double_as_longlong(a) == __double_as_longlong(b) || (a == 0.0 && b == 0.0);   // (+0 / -0: see div_const)
+    if (!same) atomicAdd(mismatches, 1ull);
+}
+
+cudaError_t launch_div_const_check(long long n, const double *x, double c, double rc, unsigned long long *mismatches, cudaStream_t s)
+{
+    div_const_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, x, c, rc, mismatches);
+    return cudaGetLastError();
 }
 
 // ============================================================================

@@ -32,6 +32,7 @@ cudaError_t launch_generic(const DevModel &, const CallGases &, const KernelArgs
 template <typename Real>
 cudaError_t launch_indices(const DevModel &, const GasRef *lut, int ncol, int nlay, const Real *plev, const Real *tlay,
                            int *ip0, double *pw1, int *it0, double *tw1, int *iv0, double *vw1, cudaStream_t);
+cudaError_t launch_div_const_check(long long n, const double *x, double c, double rc, unsigned long long *mismatches, cudaStream_t);
 cudaError_t launch_planck_indices(const DevModel &, long long n, const double *T, int *it0, double *w1, cudaStream_t);
 // Geometry of a walk-kernel launch over `ntile` 16-column tiles on a device with `sms` SMs: tiles per chunk (1 or 2)
 // and blocks per g-group; block b walks chunks b, b + blocks, ...  Pure host arithmetic.

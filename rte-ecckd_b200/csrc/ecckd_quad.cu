@@ -139,9 +139,11 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 // R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
 // L      positions (layers) per hand-off: record slots and staging tiles change hands in groups of L, so that the
 //        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
+// KBALU  widen the fp32 rows of the varying gases on the integer pipe instead of with F2F (16 lanes/clk/SM: 8 cycles of the
+//        conversion unit per warp instruction, shared with the index warps' MUFU and the SW ssa division)
 // EARLYREC  read the record of the next position at the top of the iteration (ahead of the arithmetic) instead of after it
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC, bool KBALU>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -294,7 +296,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 double a0, a1;
                 int it = planck_index(m, tl, a0, a1);
                 const float2 *tl_p = spl2 + (max(it, 1) - 1);
-                const Real l0 = (Real)__ddiv_rn(a0, m.pi), l1 = (Real)__ddiv_rn(a1, m.pi);
+                const Real l0 = (Real)div_const(a0, m.pi, m.r_pi), l1 = (Real)div_const(a1, m.pi, m.r_pi);
                 const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
                 char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
                 // g-points in batches of GB: all table reads of a batch are issued before its arithmetic and its
@@ -303,7 +305,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (has_lev) {
                     it = planck_index(m, tv, a0, a1);
                     const float2 *tv_p = spl2 + (max(it, 1) - 1);
-                    const Real v0 = (Real)__ddiv_rn(a0, m.pi), v1 = (Real)__ddiv_rn(a1, m.pi);
+                    const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
                     char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
                     char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
                     for (int gq = 0; gq < ng; gq += GB) {
@@ -349,7 +351,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     double a0, a1;
                     const int it = planck_index(m, (double)a.tsfc[colp], a0, a1);
                     const int r = max(it, 1) - 1;
-                    const Real s0 = (Real)__ddiv_rn(a0, m.pi), s1 = (Real)__ddiv_rn(a1, m.pi);
+                    const Real s0 = (Real)div_const(a0, m.pi, m.r_pi), s1 = (Real)div_const(a1, m.pi, m.r_pi);
                     if (cc < ncol)
                         for (int gq = 0; gq < ng; ++gq) {
                             const float2 ps = spl2[gq * S_ + r];
@@ -588,7 +590,9 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 t = fma_(cur.wv[0].x, bm, t);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    const Real bv = bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
+                    const Real bv = KBALU ? bil4(c0, c1, c2, c3, widen_<Real>(kb[v][0][i], true), widen_<Real>(kb[v][1][i], true),
+                                                 widen_<Real>(kb[v][2][i], true), widen_<Real>(kb[v][3][i], true))
+                                          : bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
                     const Real wgt = ((v + 1) & 1) ? cur.wv[(v + 1) >> 1].y : cur.wv[(v + 1) >> 1].x;
                     t = fma_(wgt, bv, t);
                 }
@@ -696,7 +700,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false, bool KBALU = false>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -706,7 +710,7 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
                         (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC>;
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, KBALU>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
@@ -727,17 +731,14 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
-        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC
-        if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false>(m, cg, a, mix, sms, s);
-        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false>(m, cg, a, mix, sms, s);
-        if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 5) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 72, 88, false, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, false, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 7) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 72, 72, true, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 8) return launch_quad_t<Real, SW, 1, false, 16, 6, 192, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 9) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false, 1, 0, true>(m, cg, a, mix, sms, s);
-        if (v == 10) return launch_quad_t<Real, SW, 1, false, 16, 3, 176, 64, 96, false, 2, 0, false>(m, cg, a, mix, sms, s);
+        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC KBALU
+        if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, false>(m, cg, a, mix, sms, s);
+        if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, false>(m, cg, a, mix, sms, s);
+        if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        if (v == 5) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        if (v == 7) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 96, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
     }
 #endif
     // Production instantiations, as measured on B200 (tools/exp_quad.sh):

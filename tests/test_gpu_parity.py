@@ -124,6 +124,41 @@ def test_indices_are_bit_exact(key, dev, gpu_models, c_oracles):
             assert np.max(np.abs(got[k] - ref[k])) <= 2e-13, k
 
 
+def test_constant_divisor_division_is_the_ieee_quotient(dev, ck_models):
+    """The index arithmetic divides by per-model constants as q0 = x*RN(1/c), q = fma(fma(-c, q0, x), RN(1/c), q0).
+    That must be the correctly rounded quotient, bit for bit, for every divisor the three ck files produce (and a few
+    awkward ones): 2^22 dividends each -- random over the ranges the algorithm sees, plus zeros, infinities, NaN and
+    neighbours of integer quotients (where an index would flip)."""
+    import ctypes as C
+    from ecckd_b200 import _abi
+    lib = _abi.load_library()
+    g = torch.Generator(device=dev).manual_seed(7)
+    divisors = {3.0, 1.0 / 3.0, 7.0, 1e-3, 123456.789, float(np.float64(np.float32(3.14159265359)))}
+    for m in ck_models.values():
+        divisors.add(float(m.log_pressure[1] - m.log_pressure[0]))
+        divisors.add(float(m.temperature[1, 0] - m.temperature[0, 0]))
+        if not m.shortwave:
+            divisors.add(float(m.temperature_planck[1] - m.temperature_planck[0])); divisors.add(float(m.temperature_planck[0]))
+        for tab in m.absorption:
+            if tab.mole_fraction is not None:
+                divisors.add(float(np.log(tab.mole_fraction[1] / tab.mole_fraction[0])))
+    n = 1 << 22
+    for c in sorted(divisors):
+        x = torch.cat([
+            (torch.rand(n // 4, generator=g, device=dev, dtype=torch.float64) - 0.5) * 60.0,          # log-pressure differences
+            (torch.rand(n // 4, generator=g, device=dev, dtype=torch.float64) - 0.3) * 400.0,         # temperature differences
+            torch.exp((torch.rand(n // 4, generator=g, device=dev, dtype=torch.float64) - 0.5) * 200.0),
+            # quotients next to integers: x = c * k * (1 + j ulp)
+            c * torch.randint(1, 64, (n // 4,), generator=g, device=dev).double()
+              * (1.0 + (torch.randint(-3, 4, (n // 4,), generator=g, device=dev).double() * 2.220446049250313e-16)),
+            torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1e-310, 1e308, -1e308], device=dev, dtype=torch.float64)])
+        bad = C.c_uint64(123)
+        err = C.create_string_buffer(_abi.ERRLEN)
+        rc = lib.ecckd_debug_div_const(x.numel(), x.data_ptr(), c, C.byref(bad), err)
+        assert rc == _abi.OK, err.value
+        assert bad.value == 0, f"divisor {c!r}: {bad.value} of {x.numel()} quotients differ from the IEEE division"
+
+
 def test_planck_indices_bit_exact(dev, gpu_models, c_oracles):
     T = np.concatenate([np.linspace(90, 420, 4001), [120.0, 119.99999999, 350.0, 350.00000001, 121.0]])
     it_ref, w_ref = c_oracles["lw_fsck"].planck_indices(T)
