@@ -139,11 +139,11 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 // R      layers in the record ring, NBUF staging tiles, RC / RI / RH registers of compute / index / helper warps
 // L      positions (layers) per hand-off: record slots and staging tiles change hands in groups of L, so that the
 //        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
-// KBALU  widen the fp32 rows of the varying gases on the integer pipe instead of with F2F (16 lanes/clk/SM: 8 cycles of the
-//        conversion unit per warp instruction, shared with the index warps' MUFU and the SW ssa division)
+// HIDX   shortwave: the three helper warps (no Planck role there) join the index role -- 7 index warps.  Measured: no
+//        change (2.11 vs 2.13 ms on the same box): the index role is not what the shortwave waits for.  Off.
 // EARLYREC  read the record of the next position at the top of the iteration (ahead of the arithmetic) instead of after it
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC, bool KBALU>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC, bool HIDX>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -160,6 +160,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     static_assert(R % L == 0 && L <= kQNI, "record ring: whole groups; every position of a group comes from a different index warp");
+    // Shortwave has no Planck role: with the g = 0 plane leaving through the TMA unit its three helper warps have nothing
+    // to do and join the index role (7 index warps: the index arithmetic is a chain of ~140 dependent fp64 operations
+    // per position and warp, 9.6 cycles each).  toa_src is written by the index warp that handles a tile's first layer.
+    constexpr bool HELPERS_INDEX = HIDX;
+    static_assert(!HIDX || (SW && ZERO_BY_TMA), "only the shortwave's helper warps are free, and only when the TMA unit writes the g = 0 plane");
+    constexpr int NIW = HELPERS_INDEX ? kQNI + kQNH - 1 : kQNI;      // index warps
+    static_assert(!HELPERS_INDEX || RH >= RI, "helper warps that run the index role need its registers");
     unsigned char *stage = smem_raw;                                           // [NBUF][L][NOUT][TILEB]  (1024-byte aligned)
     unsigned char *zero_tile = stage + (size_t)NBUF * L * NOUT * TILEB;        // SW: source of the g = 0 plane
     RecT *recs = reinterpret_cast<RecT *>(zero_tile + (SW ? BOXB : 0));        // [R]
@@ -201,10 +208,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
     __syncthreads();
 
+    int iw = -1;                                               // index-role id of this warp (-1: another role)
     // ================================ helper warpgroup ================================
     if (warp >= kQNCW + kQNI) {
         reg_dec<RH>();
         const int hw = warp - (kQNCW + kQNI);
+        if (HELPERS_INDEX && hw >= 1) iw = kQNI + hw - 1;
+        else {
         if (ECCKD_DBG(128) && hw == 0) return;   // experiment: Planck warps only
         if (hw == 0) {
             // ---- store warp: staging tiles -> cp.async.bulk.tensor stores ----
@@ -361,13 +371,16 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
         }
         return;
+        }
     }
 
     // ================================ index warps =====================================
-    if (warp >= kQNCW) {
+    if (warp >= kQNCW && warp < kQNCW + kQNI) {
         reg_dec<RI>();
+        iw = warp - kQNCW;
+    }
+    if (iw >= 0) {
         if (ECCKD_DBG(128)) return;
-        const int iw = warp - kQNCW;
         int ts = 0, j = iw;                                    // position s = ts * nlay + j
         while (j >= nlay) { j -= nlay; ++ts; }
         int slot = iw % R, n = iw / R;                          // ring slot of s and how often it has been used before
@@ -397,18 +410,18 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             for (int v = 0; v < NV + NX; ++v)
                 if (v < nvar) { const GasRef &gr = cg.g[cg.var_gas[v]]; pf(static_cast<const Real *>(gr.vmr) + col * gr.col_stride + (long long)j_ * gr.lay_stride); }
         };
-        int pj = j, pts = ts;                                   // position kPF * kQNI ahead of s
-        for (int q2 = 0; q2 < kPF; ++q2) { pj += kQNI; while (pj >= nlay) { pj -= nlay; ++pts; } }
+        int pj = j, pts = ts;                                   // position kPF * NIW ahead of s
+        for (int q2 = 0; q2 < kPF; ++q2) { pj += NIW; while (pj >= nlay) { pj -= nlay; ++pts; } }
         In nxt;
         if (iw < S) fetch(ts, j, nxt);
-        for (int s = iw; s < Spad; s += kQNI) {
+        for (int s = iw; s < Spad; s += NIW) {
             const In in = nxt;
             {
-                int j2 = j + kQNI, ts2 = ts;
+                int j2 = j + NIW, ts2 = ts;
                 while (j2 >= nlay) { j2 -= nlay; ++ts2; }
-                if (s + kQNI < S) fetch(ts2, j2, nxt);
-                if (!ECCKD_DBG(512) && s + kPF * kQNI < S) prefetch(pts, pj);
-                pj += kQNI; while (pj >= nlay) { pj -= nlay; ++pts; }
+                if (s + NIW < S) fetch(ts2, j2, nxt);
+                if (!ECCKD_DBG(512) && s + kPF * NIW < S) prefetch(pts, pj);
+                pj += NIW; while (pj >= nlay) { pj -= nlay; ++pts; }
             }
             P c01, c23, lutw, wv[NW2], aux;
             int2 key;
@@ -453,6 +466,11 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     lutw = make_pair_<P>(wd, v1);
                 }
             }
+            if (HELPERS_INDEX && j == 0 && s < S && a.out2d) {        // toa_src(:, g) = solar_irradiance(g)   :468-472
+                const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+                if (cc < ncol)
+                    for (int gq = 0; gq < min(kGP, ngpt - g0); ++gq) a.out2d[cc + (long long)ncol * (g0 + gq)] = (Real)m.solar[g0 + gq];
+            }
             if (n >= 1) mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap);
             RecT &rc = recs[slot];
             rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane] = key;
@@ -460,8 +478,8 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             for (int v = 0; v < NW2; ++v) rc.w[v][lane] = wv[v];
             __syncwarp();
             if (lane == 0) mbar_arrive(&rec_full[slot / L]);
-            j += kQNI; while (j >= nlay) { j -= nlay; ++ts; }
-            slot += kQNI; while (slot >= R) { slot -= R; ++n; }
+            j += NIW; while (j >= nlay) { j -= nlay; ++ts; }
+            slot += NIW; while (slot >= R) { slot -= R; ++n; }
         }
         return;
     }
@@ -475,6 +493,8 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     // table pointers of this lane (rows are stored permuted, see walk_pos32 / walk_pos64): 4-byte rows hold the lane's
     // g-points q, q+8, q+16, q+24 as one 16-byte vector at 4q; 8-byte rows as two vectors at 2q and 16 + 2q
     constexpr int LQ = sizeof(LutT) == 8 ? 2 : 4, MQ = sizeof(Real) == 8 ? 2 : 4;
+    // (caching the varying gases' rows at full width from the fp64 tables, or widening them on the integer pipe, instead
+    //  of F2F in the FMA chain: both measured, neither faster)
     const float *wbil = m.wbil32 + (size_t)grp * m.nslot * kSlab + 4 * q;
     const LutT *wlut = (LUT32 ? reinterpret_cast<const LutT *>(m.wlut32) : reinterpret_cast<const LutT *>(TableOf<Real>::wlut(m))) +
                        (size_t)grp * m.nv_lut * kSlab + LQ * q;
@@ -590,9 +610,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 t = fma_(cur.wv[0].x, bm, t);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    const Real bv = KBALU ? bil4(c0, c1, c2, c3, widen_<Real>(kb[v][0][i], true), widen_<Real>(kb[v][1][i], true),
-                                                 widen_<Real>(kb[v][2][i], true), widen_<Real>(kb[v][3][i], true))
-                                          : bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
+                    const Real bv = bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]);
                     const Real wgt = ((v + 1) & 1) ? cur.wv[(v + 1) >> 1].y : cur.wv[(v + 1) >> 1].x;
                     t = fma_(wgt, bv, t);
                 }
@@ -700,7 +718,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false, bool KBALU = false>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false, bool HIDX = false>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -710,7 +728,7 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
                         (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, KBALU>;
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, HIDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
@@ -731,14 +749,15 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
-        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC KBALU
+        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC HIDX
         if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, false>(m, cg, a, mix, sms, s);
         if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, false>(m, cg, a, mix, sms, s);
-        if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
-        if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
-        if (v == 5) return launch_quad_t<Real, SW, 1, true, 16, 6, 152, 80, 128, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
-        if (v == 6) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, false, 1, 0, false, true>(m, cg, a, mix, sms, s);
-        if (v == 7) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 96, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        if constexpr (SW) {
+            if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+            if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+            if (v == 5) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 72, 72, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+            if (v == 6) return launch_quad_t<Real, SW, 1, false, 32, 6, 184, 64, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
+        }
     }
 #endif
     // Production instantiations, as measured on B200 (tools/exp_quad.sh):
