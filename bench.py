@@ -188,6 +188,45 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line))
 
 
+def bind_near_gpu(local_rank: int, world: int) -> dict:
+    """Pin this rank's host threads to the NUMA node its GPU hangs off (sysfs: the GPU's PCI device -> numa_node -> cpulist),
+    or, when the topology is not exposed, to an equal slice of the cores.  Pinned host buffers are then first-touched on
+    that node: with every rank allocating on node 0 the e2e (host-array) path of 8 ranks shared one memory controller."""
+    info = {"numa_node": None, "cpus": None}
+    if world <= 1:          # one rank: leave the process unbound (the CPU baseline then has every host core)
+        return info
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        node = None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True).stdout.strip()
+            bus = out.lower().replace("00000000:", "0000:") if out else None
+        if bus:
+            path = f"/sys/bus/pci/devices/{str(bus).lower()}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+        cpus = None
+        if node is not None and node >= 0:
+            cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            cpus = set()
+            for part in cl.split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+        if not cpus and world > 1:
+            allc = sorted(os.sched_getaffinity(0))
+            per = max(1, len(allc) // world)
+            cpus = set(allc[local_rank * per:(local_rank + 1) * per]) or set(allc)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception as exc:
+        info["error"] = str(exc)
+    return info
+
+
 def fortran_probe() -> dict:
     """Is there a Fortran compiler on THIS box (probe at run time)?  With one, `make -C oracle/ref` builds the
     unmodified reference against stub rte-rrtmgp modules -- but only next to /root/reference, which the GPU box lacks."""
@@ -304,6 +343,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_near_gpu(local_rank, world)     # before any pinned allocation: first-touch puts the e2e buffers on that node
 
     if args.total_cols > 0:                     # strong scaling: contiguous shards of one global grid (configs[4])
         col_base, c1 = sharding.shard_columns(args.total_cols, world, rank)
@@ -508,7 +548,7 @@ def main() -> None:
                "columns_per_step": ne, "block_cols": EB, "ms_per_step": dt * 1e3,
                "api": "ecckd_gas_optics_{lw,sw}_host_f64 (pinned host arrays, H2D + kernels + D2H per column block; the caller blocks "
                       "its columns like the reference driver, so every copy is contiguous)",
-               "pcie_d2h_GBps": d2h / dt / 1e9}
+               "pcie_d2h_GBps": d2h / dt / 1e9, "host_binding": numa}
         if rank == 0 and not args.no_extras:
             try:    # the same step on PAGEABLE host arrays (what a Fortran host model passes; the library page-locks them per call)
                 pg = lambda a: np.asfortranarray(np.array(a))
