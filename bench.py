@@ -575,6 +575,67 @@ def main() -> None:
             except Exception as exc:
                 extras["e2e_pageable_error"] = str(exc)
 
+    # ---- second e2e figure (row N1): the fluxes, not the optical properties, cross PCIe ----------------------------
+    # pinned host inputs -> H2D -> gas optics + device flux solvers (ecckd_rte_{lw,sw}_f64) -> D2H of five (ncol, nlay+1)
+    # flux arrays per block.
+    e2e_fluxes = None
+    if not args.no_e2e and not args.no_extras:
+        try:
+            nf = min(ncol, 1 << 18)                       # a quarter of the 1M-column step: it is a rate
+            FB = min(B, nf)
+            nfb = (nf + FB - 1) // FB
+            keys = ("plev", "tlay", "tlev", "h2o", "o3")
+            hin = []
+            for b in range(nfb):
+                nb = min(FB, nf - b * FB)
+                atm = synthetic.make_atmosphere(nb, NLAY, col0=col_base + b * FB, device=dev)
+                hc = {k: getattr(atm, k).t().contiguous().cpu().pin_memory() for k in keys}      # (n, ncol) contiguous == Fortran (ncol, n)
+                hc["tsfc"] = atm.tsfc.cpu().pin_memory()
+                hin.append((nb, hc, atm.scalars))
+                del atm
+            hflux = [torch.empty((5, NLAY + 1, FB), dtype=torch.float64).pin_memory() for _ in range(2)]
+            o_lw = {k: FE((FB, NLAY, NG_LW), torch.float64, dev) for k in ("tau", "lay_source", "lev_source_inc", "lev_source_dec")}
+            o_lw["sfc_source"] = FE((FB, NG_LW), torch.float64, dev)
+            o_sw = {k: FE((FB, NLAY, NG_SW), torch.float64, dev) for k in ("tau", "ssa", "g")}
+            o_sw["toa_src"] = FE((FB, NG_SW), torch.float64, dev)
+            h2d_f = sum(8 * nb * (3 * (NLAY + 1) - 1 + 2 * NLAY + 1) for nb, _, _ in hin)
+            d2h_f = sum(8 * nb * 5 * (NLAY + 1) for nb, _, _ in hin)
+
+            def flux_step():
+                for i, (nb, hc, scal) in enumerate(hin):
+                    dv = {k: v.to(dev, non_blocking=True).t() for k, v in hc.items() if k != "tsfc"}
+                    tsfc = hc["tsfc"].to(dev, non_blocking=True)
+                    vals = dict(scal, h2o=dv["h2o"], o3=dv["o3"], no2=0.0)
+                    gl = [(g_, vals[g_]) for g_ in synthetic.GAS_ORDER]
+                    ol = o_lw if nb == FB else None
+                    osw = o_sw if nb == FB else None
+                    a_ = lw.gas_optics(None, dv["plev"], dv["tlay"], tsfc, gl, tlev=dv["tlev"], out=ol)
+                    up, dn = lw.rte_lw(a_)
+                    b_ = sw.gas_optics(None, dv["plev"], dv["tlay"], None, gl, out=osw)
+                    sup, sdn, sdr = sw.rte_sw(b_)
+                    hf = hflux[i & 1]
+                    for q_, t_ in enumerate((up, dn, sup, sdn, sdr)):
+                        hf[q_, :, :nb].copy_(t_.t(), non_blocking=True)
+                torch.cuda.synchronize()
+
+            for _ in range(2):
+                flux_step()
+            sharding.barrier()
+            k_f = max(2, min(args.steps, 3))
+            w0 = time.perf_counter()
+            for _ in range(k_f):
+                flux_step()
+            dtf = sharding.max_over_ranks((time.perf_counter() - w0) / k_f, dev)
+            sharding.barrier()
+            e2e_fluxes = {"value": nf * world * NLAY * (NG_LW + NG_SW) / dtf, "unit": UNIT,
+                          "h2d_bytes_per_step": h2d_f, "d2h_bytes_per_step": d2h_f, "columns_per_step": nf, "block_cols": FB, "ms_per_step": dtf * 1e3,
+                          "api": "pinned host inputs -> H2D -> gas_optics (device arrays) -> ecckd_rte_{lw,sw}_f64 (device flux solvers: no-scattering LW, "
+                                 "two-stream SW) -> D2H of flux_up/dn (LW) and flux_up/dn/dn_dir (SW), each (ncol, nlay+1); optical properties never leave HBM"}
+            del hin, hflux, o_lw, o_sw
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            extras["e2e_fluxes_error"] = str(exc)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -596,7 +657,7 @@ def main() -> None:
                        "ck_definitions": [os.path.basename(LW_FILE), os.path.basename(SW_FILE)],
                        "l2": "every launch streams >9 GB of outputs and 0.36 GB of inputs: far larger than the 126 MB L2, no flush needed",
                        "gases": "h2o, o3 (ncol,nlay) fields; co2, ch4, n2o, o2, cfc11, cfc12 scalars (RFMIP convention)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_sw": roofline_sw,
+            "clocks": clocks, "e2e": e2e, "e2e_fluxes": e2e_fluxes, "gpu_launches": launches, "roofline": roofline, "roofline_sw": roofline_sw,
             "roofline_f32": roofline_f32, "roofline_sw_f32": roofline_sw_f32,
             "cpu_baseline": cpu, "extras": extras,
             "split": {"lw_gptl_per_s_per_gpu": B * NLAY * NG_LW / (lw_ms * 1e-3), "sw_gptl_per_s_per_gpu": B * NLAY * NG_SW / (sw_ms * 1e-3)},

@@ -220,6 +220,21 @@ int ecckd_gas_optics_sw_host_f32(ecckd_model *model, int ncol, int nlay,
                                  float *tau, float *ssa, float *g, float *toa_src,
                                  int block_cols, char err[ECCKD_ERRLEN]);
 
+/* ---- next row N1: minimal flux solvers on the device ------------------------
+ * Not part of the ty_gas_optics boundary: they stand where the reference drivers call rte-rrtmgp's rte_lw / rte_sw
+ * (ecckd_rfmip_lw.F90:130-135, ecckd_rfmip_sw.F90:148-154) so that a device-resident pipeline -- gas optics, then
+ * fluxes -- sends (ncol, nlay+1) fluxes over PCIe instead of the (ncol, nlay, ngpt) optical properties.  Same
+ * published formulation as tests/rte_solvers.py (LW: no scattering, one quadrature angle `diffusivity` (1.66), source
+ * linear in tau, surface emissivity; SW: two-stream + adding with a direct beam at cosine `mu0`, Lambertian surface),
+ * summed over the g-points.  Device arrays in the gas-optics layout; fluxes are (ncol, nlay+1), top first, W m-2. */
+int ecckd_rte_lw_f64(ecckd_model *model, int dev_index, int ncol, int nlay, int ngpt,
+                     const double *tau, const double *lay_source, const double *lev_source_inc, const double *lev_source_dec,
+                     const double *sfc_source, double sfc_emis, double diffusivity,
+                     double *flux_up, double *flux_dn, void *stream, char err[ECCKD_ERRLEN]);
+int ecckd_rte_sw_f64(ecckd_model *model, int dev_index, int ncol, int nlay, int ngpt,
+                     const double *tau, const double *ssa, const double *g, const double *toa_src, double mu0, double sfc_albedo,
+                     double *flux_up, double *flux_dn, double *flux_dn_dir, void *stream, char err[ECCKD_ERRLEN]);
+
 /* Page-lock / release a caller array so that the host entry points above copy asynchronously.  Registration costs
  * about as much as one pass over the memory: do it once for arrays that are passed call after call (the Fortran shim
  * exposes it as a plain subroutine).  Already page-locked memory is accepted (ECCKD_OK). */

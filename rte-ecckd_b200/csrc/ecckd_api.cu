@@ -39,6 +39,8 @@ struct DevState {
     DevModel dm{};
     std::vector<void *> allocs;
     Slot slots[kSlots];
+    void *rte_scratch = nullptr;      // grow-only work space of ecckd_rte_sw_f64 (direct beam, albedo, source of the adding method)
+    size_t rte_scratch_bytes = 0;
 };
 
 // NVTX range for the profilers' timelines (H2D / table mix + walk / D2H); a no-op without an attached tool
@@ -109,6 +111,7 @@ struct ecckd_model {
                 if (s.stream) cudaStreamDestroy(s.stream);
             }
             for (void *p : d->allocs) cudaFree(p);
+            if (d->rte_scratch) cudaFree(d->rte_scratch);
         }
     }
 };
@@ -877,6 +880,48 @@ int ecckd_interpolation_indices_f64(ecckd_model *M, int dev_index, int ncol, int
     DevState &d = *M->devs[dev_index];
     CUDA_TRY(cudaSetDevice(d.device));
     CUDA_TRY(launch_indices<double>(d.dm, has ? &lut : nullptr, ncol, nlay, plev, tlay, ip0, pw1, it0, tw1, iv0, vw1, (cudaStream_t)stream));
+    return ECCKD_OK;
+}
+
+int ecckd_rte_lw_f64(ecckd_model *M, int dev_index, int ncol, int nlay, int ngpt, const double *tau, const double *lay_source,
+                     const double *lev_source_inc, const double *lev_source_dec, const double *sfc_source, double sfc_emis,
+                     double diffusivity, double *flux_up, double *flux_dn, void *stream, char err[ECCKD_ERRLEN])
+{
+    if (err) err[0] = '\0';
+    if (!M || dev_index < 0 || dev_index >= (int)M->devs.size()) { set_err(err, "ecckd: bad model/device"); return ECCKD_ERR_ARG; }
+    if (ncol < 0 || nlay < 0 || ngpt < 1) { set_err(err, "ecckd: bad extent"); return ECCKD_ERR_ARG; }
+    if (ncol == 0 || nlay == 0) return ECCKD_OK;
+    if (!tau || !lay_source || !lev_source_inc || !lev_source_dec || !sfc_source || !flux_up || !flux_dn) { set_err(err, "ecckd: NULL array argument"); return ECCKD_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(M->devs[dev_index]->device));
+    NvtxRange nvtx("ecckd: rte_lw (device flux solver)");
+    CUDA_TRY(launch_rte_lw(ncol, nlay, ngpt, tau, lay_source, lev_source_inc, lev_source_dec, sfc_source, sfc_emis, diffusivity, flux_up, flux_dn,
+                           (cudaStream_t)stream));
+    return ECCKD_OK;
+}
+
+int ecckd_rte_sw_f64(ecckd_model *M, int dev_index, int ncol, int nlay, int ngpt, const double *tau, const double *ssa, const double *g,
+                     const double *toa_src, double mu0, double sfc_albedo, double *flux_up, double *flux_dn, double *flux_dn_dir,
+                     void *stream, char err[ECCKD_ERRLEN])
+{
+    if (err) err[0] = '\0';
+    if (!M || dev_index < 0 || dev_index >= (int)M->devs.size()) { set_err(err, "ecckd: bad model/device"); return ECCKD_ERR_ARG; }
+    if (ncol < 0 || nlay < 0 || ngpt < 1 || !(mu0 > 0.0)) { set_err(err, "ecckd: bad extent / mu0"); return ECCKD_ERR_ARG; }
+    if (ncol == 0 || nlay == 0) return ECCKD_OK;
+    if (!tau || !ssa || !g || !toa_src || !flux_up || !flux_dn || !flux_dn_dir) { set_err(err, "ecckd: NULL array argument"); return ECCKD_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(M->devs[dev_index]->device));
+    NvtxRange nvtx("ecckd: rte_sw (device flux solver)");
+    // Work space: three (ncol, nlay+1, ngpt) arrays, kept per device and only ever grown (a stream-ordered allocation of
+    // several GB per call would be handed back to the driver at every synchronisation).  Calls on one device must
+    // therefore not overlap on different streams.
+    DevState &d = *M->devs[dev_index];
+    const size_t need = rte_sw_scratch_bytes(ncol, nlay, ngpt);
+    if (d.rte_scratch_bytes < need) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (d.rte_scratch) { CUDA_TRY(cudaFree(d.rte_scratch)); d.rte_scratch = nullptr; d.rte_scratch_bytes = 0; }
+        CUDA_TRY(cudaMalloc(&d.rte_scratch, need));
+        d.rte_scratch_bytes = need;
+    }
+    CUDA_TRY(launch_rte_sw(ncol, nlay, ngpt, tau, ssa, g, toa_src, mu0, sfc_albedo, d.rte_scratch, flux_up, flux_dn, flux_dn_dir, (cudaStream_t)stream));
     return ECCKD_OK;
 }
 

@@ -32,6 +32,12 @@ cudaError_t launch_generic(const DevModel &, const CallGases &, const KernelArgs
 template <typename Real>
 cudaError_t launch_indices(const DevModel &, const GasRef *lut, int ncol, int nlay, const Real *plev, const Real *tlay,
                            int *ip0, double *pw1, int *it0, double *tw1, int *iv0, double *vw1, cudaStream_t);
+// N1: minimal broadband flux solvers on the device (ecckd_rte.cu); arrays as the gas optics wrote them
+cudaError_t launch_rte_lw(int ncol, int nlay, int ngpt, const double *tau, const double *lay, const double *inc, const double *dec,
+                          const double *sfc, double emis, double D, double *flux_up, double *flux_dn, cudaStream_t);
+size_t rte_sw_scratch_bytes(int ncol, int nlay, int ngpt);
+cudaError_t launch_rte_sw(int ncol, int nlay, int ngpt, const double *tau, const double *ssa, const double *g, const double *toa,
+                          double mu0, double alb_sfc, void *scratch, double *flux_up, double *flux_dn, double *flux_dir, cudaStream_t);
 cudaError_t launch_div_const_check(long long n, const double *x, double c, double rc, unsigned long long *mismatches, cudaStream_t);
 cudaError_t launch_planck_indices(const DevModel &, long long n, const double *T, int *it0, double *w1, cudaStream_t);
 // Geometry of a walk-kernel launch over `ntile` 16-column tiles on a device with `sms` SMs: tiles per chunk (1 or 2)

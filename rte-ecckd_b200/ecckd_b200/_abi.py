@@ -70,6 +70,8 @@ _SIGS = {
     "ecckd_get_temp_max": (C.c_double, [_vp]),
     "ecckd_get_total_solar_irradiance": (C.c_double, [_vp]),
     "ecckd_interpolation_indices_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _cp, _views, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _cp]),
+    "ecckd_rte_lw_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _cp]),
+    "ecckd_rte_sw_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _cp]),
     "ecckd_debug_div_const": (_i, [C.c_int64, _vp, C.c_double, C.POINTER(C.c_uint64), _cp]),
     "ecckd_planck_indices_f64": (_i, [_vp, _i, C.c_int64, _vp, _vp, _vp, _vp, _cp]),
 }

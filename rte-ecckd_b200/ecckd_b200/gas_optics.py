@@ -391,6 +391,40 @@ class GasOpticsEcckd:
             raise EcckdError(rc, err.value.decode(), partial=out)
         return out
 
+    # -- next row N1: flux solvers on the device (what the reference drivers get from rte-rrtmgp) ---------------------
+    def rte_lw(self, out: dict, sfc_emis: float = 0.98, diffusivity: float = 1.66, dev_index: int = 0, stream=None):
+        """Broadband LW fluxes (up, down), each (ncol, nlay+1), from the fp64 device tensors gas_optics returned."""
+        import torch
+        tau = out["tau"]
+        ncol, nlay, ngpt = tau.shape
+        up, dn = fortran_empty((ncol, nlay + 1), torch.float64, tau.device), fortran_empty((ncol, nlay + 1), torch.float64, tau.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(tau.device).cuda_stream
+        err = C.create_string_buffer(_abi.ERRLEN)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        rc = self._lib.ecckd_rte_lw_f64(self._h, dev_index, ncol, nlay, ngpt, P(tau), P(out["lay_source"]), P(out["lev_source_inc"]),
+                                        P(out["lev_source_dec"]), P(out["sfc_source"]), sfc_emis, diffusivity, P(up), P(dn), stream, err)
+        if rc != _abi.OK:
+            raise EcckdError(rc, err.value.decode())
+        return up, dn
+
+    def rte_sw(self, out: dict, mu0: float = 0.6, sfc_albedo: float = 0.2, dev_index: int = 0, stream=None):
+        """Broadband SW fluxes (up, down total, down direct), each (ncol, nlay+1), from gas_optics' fp64 device tensors."""
+        import torch
+        tau = out["tau"]
+        ncol, nlay, ngpt = tau.shape
+        mk = lambda: fortran_empty((ncol, nlay + 1), torch.float64, tau.device)
+        up, dn, dr = mk(), mk(), mk()
+        if stream is None:
+            stream = torch.cuda.current_stream(tau.device).cuda_stream
+        err = C.create_string_buffer(_abi.ERRLEN)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        rc = self._lib.ecckd_rte_sw_f64(self._h, dev_index, ncol, nlay, ngpt, P(tau), P(out["ssa"]), P(out["g"]), P(out["toa_src"]),
+                                        mu0, sfc_albedo, P(up), P(dn), P(dr), stream, err)
+        if rc != _abi.OK:
+            raise EcckdError(rc, err.value.decode())
+        return up, dn, dr
+
     def interpolation_indices(self, plev, tlay, lut_gas: Optional[str] = None, lut_vmr=None, dev_index: int = 0) -> dict:
         """Debug: 1-based ip0/it0/iv0 and upper weights from the kernels' own index function (device tensors)."""
         ncol, nlay = int(tlay.shape[0]), int(tlay.shape[1])

@@ -459,6 +459,35 @@ def test_downstream_fluxes_within_0p01_wm2(dtype, dev, gpu_models, ck_models, c_
     assert max(np.abs(a - b).max() for a, b in zip(sg, sr)) < 0.01
 
 
+@pytest.mark.parametrize("key", ["lw_fsck", "lw_rrtmgp", "sw_wide"])
+def test_device_flux_solvers_match_the_numpy_solvers(key, dev, gpu_models, ck_models, c_oracles):
+    """Row N1 on the device: ecckd_rte_{lw,sw}_f64 on the GPU's optical properties vs tests/rte_solvers.py on the SAME
+    arrays (<= 1e-6 W m-2: same formulation; exp() differs in the last bit between CUDA and numpy, and the linear-in-tau
+    source factor (1-t)/x - t amplifies that for thin layers), and vs the numpy solver on the ORACLE's optical
+    properties (< 0.01 W m-2, the BASELINE criterion).  lw_rrtmgp has 36 g-points: two g-passes per block."""
+    import rte_solvers
+    ncol, nlay = 70, 137
+    atm = synthetic.make_atmosphere(ncol, nlay, col0=977, device=dev)
+    go, m = gpu_models[key], ck_models[key]
+    lw = not m.shortwave
+    out = go.gas_optics(None, atm.plev, atm.tlay, atm.tsfc if lw else None, atm.gas_list(), tlev=atm.tlev if lw else None)
+    host = {k: v.cpu().numpy() for k, v in out.items()}
+    inp = atm_numpy(synthetic.make_atmosphere(ncol, nlay, col0=977))
+    ref = run_oracle(c_oracles[key], m, *inp)
+    if lw:
+        got = [t.cpu().numpy() for t in go.rte_lw(out)]
+        f = lambda d: rte_solvers.lw_fluxes(*(np.asarray(d[k], dtype=np.float64) for k in ("tau", "lay_source", "lev_source_inc", "lev_source_dec", "sfc_source")))
+    else:
+        got = [t.cpu().numpy() for t in go.rte_sw(out)]
+        f = lambda d: rte_solvers.sw_fluxes(*(np.asarray(d[k], dtype=np.float64) for k in ("tau", "ssa", "g", "toa_src")))
+    same, orc = f(host), f(ref)
+    for a, b, c in zip(got, same, orc):
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() <= 1e-6, f"{key}: device solver vs numpy solver on the same optical properties: {np.abs(a - b).max():.3e} W m-2"
+        assert np.abs(a - c).max() < 0.01, f"{key}: device pipeline vs oracle + numpy solver: {np.abs(a - c).max():.3e} W m-2"
+    assert got[0].max() > 50.0                                       # real fluxes, not zeros
+
+
 def test_in_process_multi_device_host_sharding(dev):
     """A model replicated on every visible GPU: the host entry points shard the columns over the devices (no
     collective) and reproduce the single-device result bitwise.  Needs >= 2 GPUs (verified on a 2-GPU box with
