@@ -7,18 +7,17 @@
 // with ONE fused pass per call: interpolation indices once per (column, layer),
 // all gases accumulated in registers, every output element stored exactly once.
 //
-// Two kernels:
-//   walk_kernel    -- the product path.  One warp walks one column top to bottom,
-//                     lanes = g-points.  Lane-distributed index arithmetic (lane l
-//                     does layer j0+l, results broadcast through shared memory),
-//                     coefficient corner rows cached in registers and reloaded
-//                     only when (ip0,it0[,iv0]) move, results transposed through a
-//                     padded shared-memory tile so global stores are full 128-byte
-//                     column-contiguous lines.
-//   generic_kernel -- thread per (column, layer), loop over g; handles any gas mix
-//                     (several LUT gases, >8 bilinear gases, tables with negative
-//                     entries) with the reference's per-g clamp.  Also the
-//                     cross-check of walk_kernel in the GPU tests.
+// This file: the fallback kernels, the per-call table mixing and the launch dispatch.  The product kernel is
+// quad_kernel in ecckd_quad.cu (four columns per compute warp, TMA tensor stores).
+//   walk_kernel    -- round 1's product kernel, now the fallback for calls the quad kernel cannot map (odd column
+//                     counts, unaligned outputs, more than seven varying gases).  A warp-specialised pipeline in a
+//                     persistent block: index warps (lane = layer) -> compute warps (one column each, lanes =
+//                     g-points, corner rows cached in registers) -> TMA store warp or writer warps; Planck warps
+//                     (lanes = columns) write the sources directly.  Same arithmetic as quad_kernel, bit for bit.
+//   generic_kernel -- thread per (column, layer), loop over g; handles any gas mix (several LUT gases, tables with
+//                     negative entries or not exact in fp32, more than 64 pressure levels) with the reference's
+//                     per-g clamp.  Also an independent second formulation in the GPU tests.
+//   mix_kernel     -- per call: gases with a call-constant weight factor pre-mixed into one table.
 #include "ecckd_device.cuh"
 #include "ecckd_kernels.h"
 #include "ecckd_pipeline.cuh"

@@ -174,3 +174,34 @@ def test_walk_plan_covers_every_tile_exactly_once(shortwave, sms):
         assert (seen == 1).all(), f"ncol={ncol}: tiles walked {seen.min()}..{seen.max()} times"
         # balance: the longest block is within one chunk of the ideal share
         assert longest <= -(-ntile // blocks) + tpc - 1 + (tpc - 1)
+
+
+def test_constant_divisor_division_in_numpy(ck_models):
+    """The device divides by per-model constants as q0 = x*RN(1/c), q = fma(fma(-c, q0, x), RN(1/c), q0) (div_const in
+    csrc/ecckd_device.cuh).  The same sequence, with the FMAs evaluated exactly in Python fractions and rounded once,
+    must return the IEEE quotient x / c for every divisor of the three ck files (the GPU test repeats this on the device
+    with 2^22 dividends per divisor)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(11)
+
+    def fma(a, b, c):        # one rounding: exact in rationals, then to the nearest double
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+    divisors = set()
+    for m in ck_models.values():
+        divisors.add(float(m.log_pressure[1] - m.log_pressure[0]))
+        divisors.add(float(m.temperature[1, 0] - m.temperature[0, 0]))
+        if not m.shortwave:
+            divisors.add(float(m.temperature_planck[1] - m.temperature_planck[0])); divisors.add(float(m.temperature_planck[0]))
+        for tab in m.absorption:
+            if tab.mole_fraction is not None:
+                divisors.add(float(np.log(tab.mole_fraction[1] / tab.mole_fraction[0])))
+    divisors.add(float(np.float64(np.float32(3.14159265359))))
+    for c in sorted(divisors):
+        rc = 1.0 / c
+        xs = np.concatenate([(rng.random(400) - 0.5) * 60.0, (rng.random(400) - 0.3) * 400.0,
+                             c * rng.integers(1, 64, 400) * (1.0 + rng.integers(-3, 4, 400) * 2.220446049250313e-16)])
+        for x in xs:
+            x = float(x)
+            q0 = x * rc
+            q = fma(fma(-c, q0, x), rc, q0)
+            assert q == x / c, (c, x)
