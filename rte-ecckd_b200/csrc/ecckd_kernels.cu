@@ -937,7 +937,7 @@ cudaError_t launch_walk(const DevModel &m, const CallGases &cg, const KernelArgs
                     if (a.out[o]) ok = ok && encode_output_map(&maps.m[o], reinterpret_cast<double *>(a.out[o]), a.ncol, a.nlay, m.ngpt);
                 if (ok) {
 #ifdef ECCKD_TUNE_WALK1
-                    // tuning build: ECCKD_WALK_VARIANT selects an alternative instantiation (tools/tune.sh)
+                    // tuning build: ECCKD_WALK_VARIANT selects an alternative instantiation (round-1 tuning sweeps; build with -DECCKD_TUNE_WALK1)
                     //   100 + RF      refill flavour RF at the default geometry
                     //   LW 1..5       2 / 4 / 6 / 8 Planck warps, 3 index warps      LW 6..8   ring of 4 / 8 / 16 tiles
                     //   SW 1..2       ring of 4 / 16 tiles      SW 3      3 index warps (20 warps: 96 registers per thread)

@@ -746,7 +746,7 @@ template <typename Real, bool SW>
 cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
 #ifdef ECCKD_TUNE
-    // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/tune.sh)
+    // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/exp_quad.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
         //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC HIDX

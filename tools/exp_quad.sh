@@ -1,4 +1,11 @@
-# tuning-build experiments for the quad kernel (make -C rte-ecckd_b200/csrc -B EXTRA=-DECCKD_TUNE)
-for v in ${VARIANTS:-0 1 2 4 6 7 8 9 10}; do for b in lw sw; do echo -n "VAR=$v "; ECCKD_QUAD_VARIANT=$v timeout -s KILL 60 python tools/prof_one.py $b f64 walk 65536 6; done; done
-for v in ${VARIANTS32:-0 4}; do for b in lw sw; do echo -n "VAR=$v "; ECCKD_QUAD_VARIANT=$v timeout -s KILL 60 python tools/prof_one.py $b f32 walk 65536 6; done; done
-for d in ${DBGS:-64 66 128}; do for b in lw; do echo -n "VAR=${DV:-6} DBG=$d "; ECCKD_QUAD_VARIANT=${DV:-6} ECCKD_DBG=$d timeout -s KILL 60 python tools/prof_one.py $b f64 walk 65536 6; done; done
+# Tuning-build experiments for the quad kernel.  Build first:  make -C rte-ecckd_b200/csrc -B EXTRA=-DECCKD_TUNE
+#   ECCKD_QUAD_VARIANT=<n>  alternative instantiation (register split, LUT width, ring sizes ...: the table next to
+#                           ECCKD_QUAD_VARIANT in csrc/ecckd_quad.cu)
+#   ECCKD_DBG=<bits>        timing experiments, results are WRONG: 1 no TMA stores, 2 index warps idle after the first ring
+#                           fill, 4 no arithmetic, 8 no cache refills, 16 no staging stores / proxy fence, 64 no Planck warps,
+#                           128 Planck warps only, 1024 Planck table widened with F2F instead of integer operations
+#   ECCKD_BLOCKS=<n>        blocks per g-group (default: one per SM)
+# Compare only numbers from ONE run of this script: the B200 boxes of the pool differ by several per cent.
+for v in ${VARIANTS:-0 1 2}; do for b in lw sw; do echo -n "VAR=$v "; ECCKD_QUAD_VARIANT=$v timeout -s KILL 60 python tools/prof_one.py $b f64 walk 65536 6; done; done
+for v in ${VARIANTS32:-0}; do for b in lw sw; do echo -n "VAR=$v "; ECCKD_QUAD_VARIANT=$v timeout -s KILL 60 python tools/prof_one.py $b f32 walk 65536 6; done; done
+for d in ${DBGS:-64 66 128}; do for b in lw; do echo -n "VAR=${DV:-0} DBG=$d "; ECCKD_QUAD_VARIANT=${DV:-0} ECCKD_DBG=$d timeout -s KILL 60 python tools/prof_one.py $b f64 walk 65536 6; done; done
