@@ -129,19 +129,19 @@ template <typename T> __device__ __forceinline__ void keep(T *&p) { asm volatile
 __device__ __forceinline__ void keep(int &v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void keep(unsigned &v) { asm volatile("" : "+r"(v)); }
 // the same barrier operations on a precomputed shared-window address (saves the generic -> shared conversion per use)
-__device__ __forceinline__ void mbar_arrive_a(unsigned addr)
+template <int OFF = 0> __device__ __forceinline__ void mbar_arrive_a(unsigned addr)
 {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0+%1];\n\t}" ::"r"(addr), "n"(OFF) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity)
+template <int OFF = 0> __device__ __forceinline__ void mbar_wait_a(unsigned addr, unsigned parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0+%2], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(addr), "r"(parity), "n"(OFF) : "memory");
 }
 __device__ __forceinline__ bool mbar_test_a(unsigned addr, unsigned parity)
 {

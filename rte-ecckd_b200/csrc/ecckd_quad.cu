@@ -32,6 +32,10 @@
 #include "ecckd_device.cuh"
 #include "ecckd_kernels.h"
 #include "ecckd_pipeline.cuh"
+#ifndef ECCKD_STORE_PEND
+#define ECCKD_STORE_PEND 0
+#endif
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -58,8 +62,9 @@ template <typename Real, int NV, int NX = 0> struct alignas(16) QRec {
     P lut[kQCols];                // LUT gas: weight (0 when it does not contribute), vmr_weight1
     P w[(NV + NX + 2) / 2][kQCols];   // weights: mixed table, varying gases 1..NV+NX (0 when clamped away)
     P aux[kQCols];                // simple_weight (SW: moles_per_layer; upside-down layers), unused
-    int2 key[kQCols];             // x: bilinear corner offset | kNegFlag; y: LUT corner offset
-};
+    struct alignas(sizeof(P)) Key { int2 k; };
+    Key key[kQCols];              // x: bilinear corner offset | kNegFlag; y: LUT corner offset (same pitch as the pairs: one
+};                                //    lane address serves every field)
 
 template <typename T> __device__ __forceinline__ T make_pair_(double a, double b);
 template <> __device__ __forceinline__ double2 make_pair_<double2>(double a, double b) { return make_double2(a, b); }
@@ -219,7 +224,14 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         if (hw == 0) {
             // ---- store warp: staging tiles -> cp.async.bulk.tensor stores ----
             if (lane == 0) {
-                int b = 0, par = 0, ts = 0, j = 0;
+                // kStorePend bulk groups stay in flight: the tile of group n - kStorePend is handed back once group n has
+                // been issued, so the TMA unit always has the next store queued while it reads a tile out
+#ifdef ECCKD_TUNE
+                const int pend = ECCKD_DBG(2048) ? 1 : ECCKD_DBG(4096) ? 2 : 0;
+#else
+                constexpr int pend = ECCKD_STORE_PEND;
+#endif
+                int b = 0, par = 0, ts = 0, j = 0, rb = 0;
                 for (int s0 = 0; s0 < S; s0 += L) {
                     mbar_wait_relaxed(&tile_full[b], par, kStoreNap);
 #pragma unroll
@@ -242,11 +254,12 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                         if (++j == nlay) { j = 0; ++ts; }
                     }
                     tma_commit();
-                    tma_wait_read<0>();                  // the tiles have been read out of shared memory: hand them back
-                    mbar_arrive(&tile_empty[b]);
+                    // the tiles have been read out of shared memory: hand them back
+                    if (pend == 0) tma_wait_read<0>(); else if (pend == 1) tma_wait_read<1>(); else tma_wait_read<2>();
+                    if (s0 >= pend * L) { mbar_arrive(&tile_empty[rb]); if (++rb == NBUF) rb = 0; }
                     if (++b == NBUF) { b = 0; par ^= 1; }
                 }
-                tma_wait_all<0>();
+                tma_wait_all<0>();                       // (nobody waits for the last kStorePend tiles)
             }
             return;
         }
@@ -473,7 +486,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             if (n >= 1) mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap);
             RecT &rc = recs[slot];
-            rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane] = key;
+            rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane].k = key;
 #pragma unroll
             for (int v = 0; v < NW2; ++v) rc.w[v][lane] = wv[v];
             __syncwarp();
@@ -514,31 +527,27 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 #pragma unroll
             for (int v = 0; v < NV; ++v) kb[v][r][i] = 0;
         }
-    int cur_pk = -1, cur_hk = -1;
     Real sigma[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) sigma[i] = SW ? (Real)m.rayleigh[min(g0 + q + 8 * i, ngpt - 1)] : (Real)0;
 
     // (re)load the register cache for corner offsets (pkoff, hkoff); every load is predicated on "this column's key
     // moved", so the four columns of the warp refill independently without divergence
-    auto refill_lut = [&](int hkoff) {
-        const bool pl = has_lut && hkoff != cur_hk;
+    auto refill_lut = [&](int hkoff, bool moved) {
+        const bool pl = has_lut && moved;
         if (!ECCKD_DBG(8)) {
             ld_rows_if(kh[0], wlut + hkoff, pl);
             ld_rows_if(kh[1], wlut + hkoff + kSlab, pl);
         }
-        cur_hk = hkoff;
     };
-    auto refill_bil = [&](int pkoff) {
-        const bool pb = pkoff != cur_pk;
+    auto refill_bil = [&](int pkoff, bool moved) {
+        const bool pb = moved;
         if (!ECCKD_DBG(8)) {
             ld_rows_if(km, wmix + pkoff, pb && has_mix);
 #pragma unroll
             for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, pb && v < nvar);
         }
-        cur_pk = pkoff;
     };
-    auto refill = [&](int pkoff, int hkoff) { refill_bil(pkoff); refill_lut(hkoff); };
 
     // staging address of this lane's first value (g-point q): row = g, 16-byte chunks XOR-swizzled with (row & 7) = q
     // exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out; value i (g-point q + 8 i) is 8 rows = 1024 bytes further
@@ -550,17 +559,18 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         st_off = q * 128 + ((warp ^ q) << 4) + cw * 4;
     }
     unsigned stage_a = smem_u32(stage) + st_off;
-    unsigned a_tfull = smem_u32(tile_full), a_tempty = smem_u32(tile_empty);
-    unsigned a_rfull = smem_u32(rec_full), a_rempty = smem_u32(rec_empty);
+    // the four barrier arrays are contiguous: one base register, the array is chosen by an immediate offset
+    unsigned a_bar = smem_u32(tile_full);
+    constexpr int B_TFULL = 0, B_TEMPTY = NBUF * 8, B_RFULL = 2 * NBUF * 8, B_REMPTY = (2 * NBUF + R / L) * 8;
     // record fields of this lane's column, as shared-window addresses relative to the ring slot
     constexpr unsigned PB = sizeof(P), RB = sizeof(RecT);
     constexpr unsigned O_C01 = 0, O_C23 = kQCols * PB, O_LUT = 2 * kQCols * PB, O_W = 3 * kQCols * PB,
                        O_AUX = (3 + NW2) * kQCols * PB, O_KEY = (4 + NW2) * kQCols * PB;
-    static_assert(O_KEY + kQCols * 8 == RB, "record layout");
-    unsigned rec_a = smem_u32(recs) + ct * PB, key_a = smem_u32(recs) + O_KEY + ct * 8;
+    static_assert(O_KEY + kQCols * PB == RB, "record layout");
+    unsigned rec_a = smem_u32(recs) + ct * PB;
     // loop invariants are pinned in registers: otherwise they are rematerialised from kernel parameters and special
     // registers in every iteration (measured in round 1, and visible in the SASS)
-    keep(stage_a); keep(a_tfull); keep(a_tempty); keep(a_rfull); keep(a_rempty); keep(rec_a); keep(key_a);
+    keep(stage_a); keep(a_bar); keep(rec_a);
     keep(wmix); keep(wlut);
 #pragma unroll
     for (int v = 0; v < NV; ++v) keep(wvar[v]);
@@ -573,16 +583,17 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         struct Cur { P c01, c23, lw, wv[NW2]; Real swt; int2 key; };
         auto load_rec = [&](int slot_, Cur &r) {
             const unsigned ra = rec_a + slot_ * RB;
-            r.key = lds_int2(key_a + slot_ * RB);
+            r.key = lds_int2(ra + O_KEY);
             r.c01 = lds_pair<P>(ra + O_C01); r.c23 = lds_pair<P>(ra + O_C23); r.lw = lds_pair<P>(ra + O_LUT);
 #pragma unroll
             for (int v = 0; v < NW2; ++v) r.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
             r.swt = SW ? lds_pair<P>(ra + O_AUX).x : (Real)0;
         };
         Cur cur, nxt;
-        mbar_wait_a(a_rfull, 0);
+        mbar_wait_a<B_RFULL>(a_bar, 0);
         load_rec(0, cur);
-        refill(cur.key.x & 0xffff, cur.key.y);
+        refill_bil(cur.key.x & 0xffff, true);
+        refill_lut(cur.key.y, true);
         nxt = cur;
         int slot = 0, rpar = 0, b = 0, tpar = 1;       // tpar: parity to wait for on tile_empty (the phase before the
                                                        // initial one counts as complete, so the first pass never blocks)
@@ -592,7 +603,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         for (int s = 0; s < Spad; ++s) {
             const int nslot_r = slot + 1 == R ? 0 : slot + 1;
             if (EARLYREC && s + 1 < Spad) {
-                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
+                if (ls == L - 1) mbar_wait_a<B_RFULL>(a_bar + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
                 load_rec(nslot_r, nxt);
             }
             const Real c0 = cur.c01.x, c1 = cur.c01.y, c2 = cur.c23.x, c3 = cur.c23.y;
@@ -654,10 +665,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             const Real swt = cur.swt;
             // the cache has been read: fetch the next position's corners under the rest of this layer's work
             if (!EARLYREC && s + 1 < Spad) {     // (the other order: record loads right in front of the refill loads)
-                if (ls == L - 1) mbar_wait_a(a_rfull + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
+                if (ls == L - 1) mbar_wait_a<B_RFULL>(a_bar + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
                 load_rec(nslot_r, nxt);
             }
-            if (s + 1 < Spad) refill(nxt.key.x & 0xffff, nxt.key.y);
+            if (s + 1 < Spad) {      // "moved" compares the whole word: a flip of kNegFlag alone reloads the same rows, harmlessly
+                refill_bil(nxt.key.x & 0xffff, nxt.key.x != cur.key.x);
+                refill_lut(nxt.key.y, nxt.key.y != cur.key.y);
+            }
             Real ssa[4];
             if (SW) {
 #pragma unroll
@@ -667,7 +681,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     ssa[i] = div_fast(ray, tau[i]);                   // :459
                 }
             }
-            if (ls == 0) mbar_wait_a(a_tempty + b * 8, tpar);
+            if (ls == 0) mbar_wait_a<B_TEMPTY>(a_bar + b * 8, tpar);
             const unsigned sa = stage_a + (b * L + ls) * (NOUT * TILEB);
             if (!ECCKD_DBG(16)) {
 #pragma unroll
@@ -681,8 +695,8 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (!ECCKD_DBG(16)) fence_proxy_async_smem();      // generic-proxy writes -> visible to the async (TMA) proxy
                 __syncwarp();
                 if (lane0) {
-                    mbar_arrive_a(a_tfull + b * 8);
-                    mbar_arrive_a(a_rempty + (slot / L) * 8);
+                    mbar_arrive_a<B_TFULL>(a_bar + b * 8);
+                    mbar_arrive_a<B_REMPTY>(a_bar + (slot / L) * 8);
                 }
                 if (++b == NBUF) { b = 0; tpar ^= 1; }
             }
@@ -731,6 +745,10 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
     auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, HIDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+#ifdef ECCKD_TUNE
+    if (getenv("ECCKD_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("ECCKD_CARVEOUT")));
+    if (getenv("ECCKD_VERBOSE")) fprintf(stderr, "quad smem %zu bytes\n", smem);
+#endif
     const int ntile = (a.ncol + kQCols - 1) / kQCols;
     int blocks = ntile < sms ? ntile : sms;
     if (blocks < 1) blocks = 1;
@@ -752,6 +770,20 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC HIDX
         if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, false>(m, cg, a, mix, sms, s);
         if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, false>(m, cg, a, mix, sms, s);
+        // shared-memory footprint (what is left of the 256 KB is the L1 that holds the table rows between columns)
+        if constexpr (SW) {
+            if (v == 10) return launch_quad_t<Real, SW, 1, false, 8, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+            if (v == 11) return launch_quad_t<Real, SW, 1, false, 8, 4, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+            if (v == 12) return launch_quad_t<Real, SW, 1, false, 16, 4, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+            if (v == 13) return launch_quad_t<Real, SW, 1, false, 8, 3, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+            if (v == 14) return launch_quad_t<Real, SW, 1, false, 8, 5, 184, 64, 64, true>(m, cg, a, mix, sms, s);
+        } else {
+            if (v == 10) return launch_quad_t<Real, SW, 1, false, 8, 6, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+            if (v == 11) return launch_quad_t<Real, SW, 1, false, 8, 4, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+            if (v == 12) return launch_quad_t<Real, SW, 1, false, 16, 4, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+            if (v == 13) return launch_quad_t<Real, SW, 1, false, 8, 3, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+            if (v == 14) return launch_quad_t<Real, SW, 1, false, 8, 5, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+        }
         if constexpr (SW) {
             if (v == 3) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
             if (v == 4) return launch_quad_t<Real, SW, 1, false, 16, 6, 176, 80, 80, true, 1, 0, false, true>(m, cg, a, mix, sms, s);
