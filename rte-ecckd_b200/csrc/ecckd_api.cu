@@ -650,11 +650,6 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
         ds->device = dev;
         DevModel &dm = ds->dm;
         dm.ngpt = t->ngpt; dm.np = t->npress; dm.nt = t->ntemp; dm.nplanck = M->nplanck;
-        dm.planck_alu_widen = 1;
-        for (float v : p32) {
-            unsigned b; std::memcpy(&b, &v, 4);
-            if (b != 0u && ((b >> 31) || ((b >> 23) & 0xff) == 0 || ((b >> 23) & 0xff) == 0xff)) dm.planck_alu_widen = 0;   // negative, subnormal, inf / NaN
-        }
         dm.sm_count = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&dm.sm_count, cudaDevAttrMultiProcessorCount, dev));
         dm.logp0 = t->log_pressure[0];

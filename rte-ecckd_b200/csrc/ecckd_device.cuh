@@ -40,7 +40,6 @@ enum Code : int { kNone = 0, kLinear = 1, kLut = 2, kRelLinear = 3 };  // :54-57
 // Device-resident packed tables (one copy per GPU, read-only after create).
 struct DevModel {
     int ngpt, np, nt, nplanck;
-    int planck_alu_widen;  // every planck_function entry is +0 or a positive normal fp32 number: widened with integer ops
     int sm_count;      // multiprocessors of the device this copy lives on (persistent-grid size)
     double logp0;      // log_pressure(1)                              :104
     double dlogp;      // log_pressure(2) - log_pressure(1)            :105

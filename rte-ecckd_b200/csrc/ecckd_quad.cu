@@ -118,18 +118,6 @@ __device__ __forceinline__ int2 lds_int2(unsigned addr)
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-// fp32 -> fp64 on the integer pipe (exact for zero and normal numbers, which is what the Planck table holds: checked at
-// model create).  F2F runs on the 16-lane conversion unit that the compute warps' table rows also need; three ALU
-// operations and a select are cheaper there than one more F2F on the critical unit.
-template <typename Real> __device__ __forceinline__ Real widen_(float f, bool alu);
-template <> __device__ __forceinline__ float widen_<float>(float f, bool) { return f; }
-template <> __device__ __forceinline__ double widen_<double>(float f, bool alu)
-{
-    if (!alu) return (double)f;
-    const unsigned b = __float_as_uint(f);
-    const unsigned hi = b ? (b >> 3) + 0x38000000u : 0u;      // rebias 127 -> 1023: (e + 896) << 20; the sign bit is zero here
-    return __hiloint2double((int)hi, (int)(b << 29));
-}
 template <typename Real> __device__ __forceinline__ void sts_(unsigned addr, Real v);
 template <> __device__ __forceinline__ void sts_<double>(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
@@ -179,7 +167,13 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     unsigned long long *tile_empty = tile_full + NBUF;
     unsigned long long *rec_full = tile_empty + NBUF;
     unsigned long long *rec_empty = rec_full + R / L;
-    float2 *spl2 = reinterpret_cast<float2 *>(rec_empty + R / L);                  // LW: Planck LUT of this g-group, [g][row] (row, row+1)
+    // LW: Planck LUT of this g-group, [g][row], 8 bytes per entry.  fp64 kernels hold the rows widened to fp64 (exact) and
+    // read rows r and r + 1 with two loads; fp32 kernels hold (row, row + 1) pairs and read both with one load.  Either
+    // way there is no conversion in the Planck warps' loop (widening there, on the conversion unit or with integer
+    // operations, was two thirds of their instructions)
+    using PlT = typename std::conditional<sizeof(Real) == 8, double, float2>::type;
+    PlT *spl = reinterpret_cast<PlT *>(rec_empty + R / L);
+    const int pl_pitch = m.nplanck + 1;                        // one zero entry behind the last row
 
     // logical warp order [compute | index | store | helpers]; hardware warp ids run the other way round because the
     // issue arbiter prefers the highest warp id: the compute warps get priority over the throughput-oriented helpers
@@ -198,14 +192,15 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tile_full[b], kQNCW); mbar_init(&tile_empty[b], 1); }
         for (int q = 0; q < R / L; ++q) { mbar_init(&rec_full[q], L); mbar_init(&rec_empty[q], kQNCW); }
     }
-    if (!SW) {   // each entry holds the row AND its upper neighbour: one 8-byte LDS fetches both interpolation operands
+    if (!SW) {
         const int np_ = m.nplanck;
-        for (int q = threadIdx.x; q < np_ * kGP; q += blockDim.x) {
+        for (int q = threadIdx.x; q < pl_pitch * kGP; q += blockDim.x) {
             const int row = q / kGP, gl = q % kGP;
             const bool gok = g0 + gl < ngpt;
-            const float p0 = gok ? m.planck32[(size_t)row * ngpt + g0 + gl] : 0.0f;
+            const float p0 = (gok && row < np_) ? m.planck32[(size_t)row * ngpt + g0 + gl] : 0.0f;
             const float p1 = (gok && row + 1 < np_) ? m.planck32[(size_t)(row + 1) * ngpt + g0 + gl] : 0.0f;
-            spl2[gl * np_ + row] = make_float2(p0, p1);
+            if constexpr (sizeof(Real) == 8) spl[gl * pl_pitch + row] = (double)p0;
+            else spl[gl * pl_pitch + row] = make_float2(p0, p1);
         }
     } else {
         for (int q = threadIdx.x; q < BOXB / 4; q += blockDim.x) reinterpret_cast<float *>(zero_tile)[q] = 0.0f;
@@ -286,9 +281,12 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         // ---- Planck warps (LW): lanes = columns, a unit is one level of one tile ----
         {
             if (ECCKD_DBG(64)) return;
-            const int S_ = m.nplanck;
+            const int S_ = pl_pitch;
+            auto rows2 = [](const PlT *p, Real &x, Real &y) {          // table rows r and r + 1 of one g-point
+                if constexpr (sizeof(Real) == 8) { x = p[0]; y = p[1]; }
+                else { const float2 v = *p; x = v.x; y = v.y; }
+            };
             const bool has_lev = a.tlev != nullptr;
-            const bool alu_cvt = m.planck_alu_widen != 0 && !ECCKD_DBG(1024);
             const int nlevu = has_lev ? nlay + 1 : nlay;          // levels 0..nlay carry a value when tlev is present
             const int nunit = nslot * nlevu;
             auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
@@ -318,7 +316,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (u + NPW < nunit) fetch(u + NPW, tl_n, tv_n);
                 double a0, a1;
                 int it = planck_index(m, tl, a0, a1);
-                const float2 *tl_p = spl2 + (max(it, 1) - 1);
+                const PlT *tl_p = spl + (max(it, 1) - 1);
                 const Real l0 = (Real)div_const(a0, m.pi, m.r_pi), l1 = (Real)div_const(a1, m.pi, m.r_pi);
                 const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
                 char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
@@ -327,22 +325,22 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 constexpr int GB = 4;
                 if (has_lev) {
                     it = planck_index(m, tv, a0, a1);
-                    const float2 *tv_p = spl2 + (max(it, 1) - 1);
+                    const PlT *tv_p = spl + (max(it, 1) - 1);
                     const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
                     char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
                     char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
                     for (int gq = 0; gq < ng; gq += GB) {
-                        float2 pl[GB], pv[GB];
+                        Real pl0[GB], pl1[GB], pv0[GB], pv1[GB];
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
                             const int so = min(gq + k, ng - 1) * S_;
-                            pl[k] = tl_p[so]; pv[k] = tv_p[so];
+                            rows2(tl_p + so, pl0[k], pl1[k]); rows2(tv_p + so, pv0[k], pv1[k]);
                         }
                         Real vl[GB], vv[GB];
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
-                            vl[k] = fma_(l1, widen_<Real>(pl[k].y, alu_cvt), mul_(l0, widen_<Real>(pl[k].x, alu_cvt)));
-                            vv[k] = fma_(v1, widen_<Real>(pv[k].y, alu_cvt), mul_(v0, widen_<Real>(pv[k].x, alu_cvt)));      // B(tlev(:,j))
+                            vl[k] = fma_(l1, pl1[k], mul_(l0, pl0[k]));
+                            vv[k] = fma_(v1, pv1[k], mul_(v0, pv0[k]));      // B(tlev(:,j))
                         }
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
@@ -355,12 +353,12 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     }
                 } else {
                     for (int gq = 0; gq < ng; gq += GB) {
-                        float2 pl[GB];
+                        Real pl0[GB], pl1[GB];
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) pl[k] = tl_p[min(gq + k, ng - 1) * S_];
+                        for (int k = 0; k < GB; ++k) rows2(tl_p + min(gq + k, ng - 1) * S_, pl0[k], pl1[k]);
 #pragma unroll
                         for (int k = 0; k < GB; ++k) {
-                            const Real vl = fma_(l1, widen_<Real>(pl[k].y, alu_cvt), mul_(l0, widen_<Real>(pl[k].x, alu_cvt)));
+                            const Real vl = fma_(l1, pl1[k], mul_(l0, pl0[k]));
                             stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && gq + k < ng);
                             p_lay += plane_b;
                         }
@@ -377,8 +375,9 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     const Real s0 = (Real)div_const(a0, m.pi, m.r_pi), s1 = (Real)div_const(a1, m.pi, m.r_pi);
                     if (cc < ncol)
                         for (int gq = 0; gq < ng; ++gq) {
-                            const float2 ps = spl2[gq * S_ + r];
-                            a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, (Real)ps.y, mul_(s0, (Real)ps.x));
+                            Real ps0, ps1;
+                            rows2(spl + gq * S_ + r, ps0, ps1);
+                            a.out2d[colp + (long long)ncol * (g0 + gq)] = fma_(s1, ps1, mul_(s0, ps0));
                         }
                 }
             }
@@ -741,7 +740,7 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
     for (int o = 0; o < (SW ? 3 : 1); ++o)
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
-                        (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * m.nplanck * kGP);
+                        (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * (m.nplanck + 1) * kGP);
     auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, HIDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
