@@ -134,9 +134,10 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 //        mbarrier round trips, the proxy fence and the warp synchronisation are paid once per L layers
 // HIDX   shortwave: the three helper warps (no Planck role there) join the index role -- 7 index warps.  Measured: no
 //        change (2.11 vs 2.13 ms on the same box): the index role is not what the shortwave waits for.  Off.
-// EARLYREC  read the record of the next position at the top of the iteration (ahead of the arithmetic) instead of after it
+// STAGED  read the KEY of the next record at the top of the iteration and refill each table's cache registers right after the
+//         arithmetic has read them for the last time, instead of refilling everything after the arithmetic
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool EARLYREC, bool HIDX>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool STAGED, bool HIDX>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -539,14 +540,16 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             ld_rows_if(kh[1], wlut + hkoff + kSlab, pl);
         }
     };
-    auto refill_bil = [&](int pkoff, bool moved) {
-        const bool pb = moved;
+    auto refill_mix = [&](int pkoff, bool moved) {
+        if (!ECCKD_DBG(8)) ld_rows_if(km, wmix + pkoff, moved && has_mix);
+    };
+    auto refill_var = [&](int pkoff, bool moved) {
         if (!ECCKD_DBG(8)) {
-            ld_rows_if(km, wmix + pkoff, pb && has_mix);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, pb && v < nvar);
+            for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, moved && v < nvar);
         }
     };
+    auto refill_bil = [&](int pkoff, bool moved) { refill_mix(pkoff, moved); refill_var(pkoff, moved); };
 
     // staging address of this lane's first value (g-point q): row = g, 16-byte chunks XOR-swizzled with (row & 7) = q
     // exactly as CU_TENSOR_MAP_SWIZZLE_128B lays the box out; value i (g-point q + 8 i) is 8 rows = 1024 bytes further
@@ -575,14 +578,16 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     for (int v = 0; v < NV; ++v) keep(wvar[v]);
 
     if (S > 0) {
-        // The record of position s + 1 is read into registers one position ahead.  EARLYREC reads it at the TOP of
-        // iteration s, ahead of the arithmetic of s (the LSU queue is in order: record loads issued behind the 28 refill
-        // loads wait for all of them, 10 % of the compute warps' stall samples) -- but the 20 extra live registers spill,
-        // and that costs more (measured: SW 1.88 -> 2.24 ms, LW 2.17 -> 2.48 ms), so the default reads it after the arithmetic.
+        // The record of position s + 1 is read into registers one position ahead, after the arithmetic of s (reading all
+        // of it ahead of the arithmetic costs 20 live registers: spills, measured slower).  STAGED reads only its KEY at the
+        // top of iteration s and refills each table's cache registers as soon as the arithmetic of s has read them for the
+        // last time (look-up table first, then the mixed table, then the varying gases) instead of all at the end: the
+        // loads get the rest of the arithmetic as a head start.
         struct Cur { P c01, c23, lw, wv[NW2]; Real swt; int2 key; };
-        auto load_rec = [&](int slot_, Cur &r) {
+        auto load_key = [&](int slot_, Cur &r) { r.key = lds_int2(rec_a + slot_ * RB + O_KEY); };
+        auto load_rec = [&](int slot_, Cur &r, bool with_key) {
             const unsigned ra = rec_a + slot_ * RB;
-            r.key = lds_int2(ra + O_KEY);
+            if (with_key) r.key = lds_int2(ra + O_KEY);
             r.c01 = lds_pair<P>(ra + O_C01); r.c23 = lds_pair<P>(ra + O_C23); r.lw = lds_pair<P>(ra + O_LUT);
 #pragma unroll
             for (int v = 0; v < NW2; ++v) r.wv[v] = lds_pair<P>(ra + O_W + v * kQCols * PB);
@@ -590,7 +595,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         };
         Cur cur, nxt;
         mbar_wait_a<B_RFULL>(a_bar, 0);
-        load_rec(0, cur);
+        load_rec(0, cur, true);
         refill_bil(cur.key.x & 0xffff, true);
         refill_lut(cur.key.y, true);
         nxt = cur;
@@ -601,15 +606,36 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         int ls = 0;                                    // position inside the hand-off group
         for (int s = 0; s < Spad; ++s) {
             const int nslot_r = slot + 1 == R ? 0 : slot + 1;
-            if (EARLYREC && s + 1 < Spad) {
+            const bool more = s + 1 < Spad;
+            if (STAGED && more) {
                 if (ls == L - 1) mbar_wait_a<B_RFULL>(a_bar + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);   // next group
-                load_rec(nslot_r, nxt);
+                load_key(nslot_r, nxt);
             }
             const Real c0 = cur.c01.x, c1 = cur.c01.y, c2 = cur.c23.x, c3 = cur.c23.y;
             const Real omv = add_((Real)1, -cur.lw.y);
             Real tau[4];
             if (ECCKD_DBG(4)) { tau[0] = c0; tau[1] = c1; tau[2] = c2; tau[3] = c3; }
-            else
+            else if constexpr (STAGED) {       // the same operations per g-point, table by table
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const Real b0 = bil4(c0, c1, c2, c3, kh[0][0][i], kh[0][1][i], kh[0][2][i], kh[0][3][i]);
+                    const Real b1 = bil4(c0, c1, c2, c3, kh[1][0][i], kh[1][1][i], kh[1][2][i], kh[1][3][i]);
+                    tau[i] = mul_(cur.lw.x, fma_(cur.lw.y, b1, mul_(omv, b0)));
+                }
+                refill_lut(nxt.key.y, more && nxt.key.y != cur.key.y);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    tau[i] = fma_(cur.wv[0].x, bil4(c0, c1, c2, c3, km[0][i], km[1][i], km[2][i], km[3][i]), tau[i]);
+                refill_mix(nxt.key.x & 0xffff, more && nxt.key.x != cur.key.x);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const Real wgt = ((v + 1) & 1) ? cur.wv[(v + 1) >> 1].y : cur.wv[(v + 1) >> 1].x;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        tau[i] = fma_(wgt, bil4(c0, c1, c2, c3, kb[v][0][i], kb[v][1][i], kb[v][2][i], kb[v][3][i]), tau[i]);
+                }
+                refill_var(nxt.key.x & 0xffff, more && nxt.key.x != cur.key.x);
+            } else
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const Real b0 = bil4(c0, c1, c2, c3, kh[0][0][i], kh[0][1][i], kh[0][2][i], kh[0][3][i]);
@@ -663,11 +689,12 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             const Real swt = cur.swt;
             // the cache has been read: fetch the next position's corners under the rest of this layer's work
-            if (!EARLYREC && s + 1 < Spad) {     // (the other order: record loads right in front of the refill loads)
+            if (STAGED) {
+                if (more) load_rec(nslot_r, nxt, false);
+            } else if (more) {
                 if (ls == L - 1) mbar_wait_a<B_RFULL>(a_bar + (nslot_r / L) * 8, nslot_r == 0 ? rpar ^ 1 : rpar);
-                load_rec(nslot_r, nxt);
-            }
-            if (s + 1 < Spad) {      // "moved" compares the whole word: a flip of kNegFlag alone reloads the same rows, harmlessly
+                load_rec(nslot_r, nxt, true);
+                // "moved" compares the whole word: a flip of kNegFlag alone reloads the same rows, harmlessly
                 refill_bil(nxt.key.x & 0xffff, nxt.key.x != cur.key.x);
                 refill_lut(nxt.key.y, nxt.key.y != cur.key.y);
             }
@@ -731,7 +758,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool EARLYREC = false, bool HIDX = false>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool STAGED = false, bool HIDX = false>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -741,7 +768,7 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
                         (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * (m.nplanck + 1) * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, EARLYREC, HIDX>;
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, STAGED, HIDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
 #ifdef ECCKD_TUNE
@@ -766,9 +793,17 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     // tuning build: ECCKD_QUAD_VARIANT selects an alternative instantiation (tools/exp_quad.sh)
     static const int v = getenv("ECCKD_QUAD_VARIANT") ? atoi(getenv("ECCKD_QUAD_VARIANT")) : 0;
     if (cg.nvar <= 1) {
-        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX EARLYREC HIDX
+        //                                  NV LUT32  R NBUF   RC   RI   RH  ZERO_BY_TMA L NX STAGED HIDX
         if (v == 1) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, false, false>(m, cg, a, mix, sms, s);
         if (v == 2) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, false, false>(m, cg, a, mix, sms, s);
+        if constexpr (SW) {
+            if (v == 20) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
+            if (v == 21) return launch_quad_t<Real, SW, 1, false, 8, 6, 184, 64, 64, true, 1, 0, true>(m, cg, a, mix, sms, s);
+        } else {
+            if (v == 20) return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, true>(m, cg, a, mix, sms, s);
+            if (v == 21) return launch_quad_t<Real, SW, 1, false, 8, 6, 168, 80, 96, false, 1, 0, true>(m, cg, a, mix, sms, s);
+            if (v == 22) return launch_quad_t<Real, SW, 1, false, 8, 6, 176, 72, 88, false, 1, 0, true>(m, cg, a, mix, sms, s);
+        }
         // shared-memory footprint (what is left of the 256 KB is the L1 that holds the table rows between columns)
         if constexpr (SW) {
             if (v == 10) return launch_quad_t<Real, SW, 1, false, 8, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
@@ -798,8 +833,10 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     //       g = 0 plane leaves through the TMA unit
     //                                          NV  LUT32   R NBUF   RC   RI   RH  ZERO_BY_TMA
     if (cg.nvar <= 1) {
-        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
-        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false>(m, cg, a, mix, sms, s);
+        // staged refills: LW 2.05 -> 2.03 ms, fp32 LW 1.97 -> 1.91, fp32 SW 1.20 -> 1.13; fp64 SW 1.61 -> 1.65 (left off there)
+        constexpr bool kStaged = !(SW && sizeof(Real) == 8);
+        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, kStaged>(m, cg, a, mix, sms, s);
     }
     if (cg.nvar <= kQuadMaxVar) {      // up to three varying gases, all cached (fp32 LUT rows to make room)
         if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
