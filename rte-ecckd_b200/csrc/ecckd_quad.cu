@@ -324,46 +324,57 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 // g-points in batches of GB: all table reads of a batch are issued before its arithmetic and its
                 // stores, so that a batch is GB independent chains instead of one serial LDS -> F2F -> FMA -> STG chain
                 constexpr int GB = 4;
+                // (rows of g-points beyond ngpt exist in the shared table and hold zeros: reads need no clamp; a whole
+                //  g-group -- the usual case -- needs no per-g-point store predicate either)
                 if (has_lev) {
                     it = planck_index(m, tv, a0, a1);
                     const PlT *tv_p = spl + (max(it, 1) - 1);
                     const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
                     char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
                     char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
-                    for (int gq = 0; gq < ng; gq += GB) {
-                        Real pl0[GB], pl1[GB], pv0[GB], pv1[GB];
+                    auto gloop = [&](auto full) {
+                        constexpr bool FULL = decltype(full)::value;
+                        const int ngl = FULL ? kGP : ng;
+                        const PlT *tlp = tl_p, *tvp = tv_p;
+                        for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_, tvp += GB * S_) {
+                            Real pl0[GB], pl1[GB], pv0[GB], pv1[GB];
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) {
-                            const int so = min(gq + k, ng - 1) * S_;
-                            rows2(tl_p + so, pl0[k], pl1[k]); rows2(tv_p + so, pv0[k], pv1[k]);
-                        }
-                        Real vl[GB], vv[GB];
+                            for (int k = 0; k < GB; ++k) { rows2(tlp + k * S_, pl0[k], pl1[k]); rows2(tvp + k * S_, pv0[k], pv1[k]); }
+                            Real vl[GB], vv[GB];
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) {
-                            vl[k] = fma_(l1, pl1[k], mul_(l0, pl0[k]));
-                            vv[k] = fma_(v1, pv1[k], mul_(v0, pv0[k]));      // B(tlev(:,j))
-                        }
+                            for (int k = 0; k < GB; ++k) {
+                                vl[k] = fma_(l1, pl1[k], mul_(l0, pl0[k]));
+                                vv[k] = fma_(v1, pv1[k], mul_(v0, pv0[k]));      // B(tlev(:,j))
+                            }
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) {
-                            const bool gk = gq + k < ng;
-                            stcs_if(reinterpret_cast<Real *>(p_lay), vl[k], ok_lay && gk);
-                            stcs_if(reinterpret_cast<Real *>(p_dec), vv[k], ok_lay && gk);            // lev_source_dec(:,j)   :424
-                            stcs_if(reinterpret_cast<Real *>(p_inc), vv[k], ok_inc && gk);            // lev_source_inc(:,j-1) :423
-                            p_lay += plane_b; p_dec += plane_b; p_inc += plane_b;
+                            for (int k = 0; k < GB; ++k) {
+                                const bool gk = FULL || gq + k < ng;
+                                stcs_if(reinterpret_cast<Real *>(p_lay), vl[k], ok_lay && gk);
+                                stcs_if(reinterpret_cast<Real *>(p_dec), vv[k], ok_lay && gk);            // lev_source_dec(:,j)   :424
+                                stcs_if(reinterpret_cast<Real *>(p_inc), vv[k], ok_inc && gk);            // lev_source_inc(:,j-1) :423
+                                p_lay += plane_b; p_dec += plane_b; p_inc += plane_b;
+                            }
                         }
-                    }
+                    };
+                    if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
                 } else {
-                    for (int gq = 0; gq < ng; gq += GB) {
-                        Real pl0[GB], pl1[GB];
+                    auto gloop = [&](auto full) {
+                        constexpr bool FULL = decltype(full)::value;
+                        const int ngl = FULL ? kGP : ng;
+                        const PlT *tlp = tl_p;
+                        for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_) {
+                            Real pl0[GB], pl1[GB];
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) rows2(tl_p + min(gq + k, ng - 1) * S_, pl0[k], pl1[k]);
+                            for (int k = 0; k < GB; ++k) rows2(tlp + k * S_, pl0[k], pl1[k]);
 #pragma unroll
-                        for (int k = 0; k < GB; ++k) {
-                            const Real vl = fma_(l1, pl1[k], mul_(l0, pl0[k]));
-                            stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && gq + k < ng);
-                            p_lay += plane_b;
+                            for (int k = 0; k < GB; ++k) {
+                                const Real vl = fma_(l1, pl1[k], mul_(l0, pl0[k]));
+                                stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && (FULL || gq + k < ng));
+                                p_lay += plane_b;
+                            }
                         }
-                    }
+                    };
+                    if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
                 }
             }
             if (a.out2d) {                                 // sfc_source(:, g) = B(tsfc)   :408-412
