@@ -136,8 +136,10 @@ template <> __device__ __forceinline__ void sts_<float>(unsigned addr, float v) 
 //        change (2.11 vs 2.13 ms on the same box): the index role is not what the shortwave waits for.  Off.
 // STAGED  read the KEY of the next record at the top of the iteration and refill each table's cache registers right after the
 //         arithmetic has read them for the last time, instead of refilling everything after the arithmetic
+// PHELP   longwave: an index warp that finds the record ring full (it is positions ahead of the compute warps) runs Planck
+//         units until its slot is free, instead of sleeping: seven warps share the Planck role instead of three
 // ZERO_BY_TMA  SW: the g = 0 plane is stored by the TMA unit from a zeroed tile instead of by the source warps
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool STAGED, bool HIDX>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC, int RI, int RH, bool ZERO_BY_TMA, int L, int NX, bool STAGED, bool HIDX, bool PHELP>
 __global__ void __launch_bounds__(kQWarps * 32, 1)
 quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGases cg, const __grid_constant__ KernelArgs<Real> a,
             const Real *__restrict__ mixtab, const __grid_constant__ TmaMaps maps)
@@ -192,6 +194,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     if (threadIdx.x == 0) {
         for (int b = 0; b < NBUF; ++b) { mbar_init(&tile_full[b], kQNCW); mbar_init(&tile_empty[b], 1); }
         for (int q = 0; q < R / L; ++q) { mbar_init(&rec_full[q], L); mbar_init(&rec_empty[q], kQNCW); }
+        if (!SW) *reinterpret_cast<unsigned *>(spl + (size_t)(m.nplanck + 1) * kGP) = 0u;       // unit_ctr
     }
     if (!SW) {
         const int np_ = m.nplanck;
@@ -209,6 +212,112 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
     }
     __syncthreads();
 
+    // ---- Planck role (LW): lanes = columns, a unit is one level of one tile.  Units are claimed from a counter in shared
+    //      memory by the Planck warps and (PHELP) by index warps that have nothing else to do ----
+    unsigned *unit_ctr = reinterpret_cast<unsigned *>(spl + (size_t)pl_pitch * kGP);
+    const int ng = min(kGP, ngpt - g0);
+    const bool has_lev = !SW && a.tlev != nullptr;
+    const int nlevu = has_lev ? nlay + 1 : nlay;          // levels 0..nlay carry a value when tlev is present
+    const int nunit = SW ? 0 : nslot * nlevu;
+    const size_t plane_b = plane * sizeof(Real);
+    const int S_ = pl_pitch;
+    auto rows2 = [](const PlT *p, Real &x, Real &y) {          // table rows r and r + 1 of one g-point
+        if constexpr (sizeof(Real) == 8) { x = p[0]; y = p[1]; }
+        else { const float2 v = *p; x = v.x; y = v.y; }
+    };
+    auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
+        const int ts = u / nlevu;
+        j = u - ts * nlevu;
+        const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
+        c_ok = cc < ncol;
+        colp = min(cc, (long long)ncol - 1);
+    };
+    auto planck_fetch = [&](int u, double &tl, double &tv) {
+        int j; long long colp; bool c_ok;
+        place(u, j, colp, c_ok);
+        tl = (double)a.tlay[colp + (long long)ncol * min(j, nlay - 1)];
+        tv = 0.0;
+        if (has_lev) tv = (double)a.tlev[colp + (long long)ncol * min(j, nlay)];
+    };
+    int my_unit = warp - (kQNCW + kQNI) - 1;              // !PHELP: the Planck warps take every third unit, no counter
+    auto claim_unit = [&]() -> int {
+        if constexpr (PHELP) {
+            unsigned u = 0;
+            if (lane == 0) u = atomicAdd(unit_ctr, 1u);
+            return (int)min(__shfl_sync(0xffffffffu, u, 0), (unsigned)nunit);
+        } else {
+            const int u = min(my_unit, nunit);
+            my_unit += NPW;
+            return u;
+        }
+    };
+    auto planck_unit = [&](int u, double tl, double tv) {
+        int j; long long colp; bool c_ok;
+        place(u, j, colp, c_ok);
+        const bool ok_lay = c_ok && j < nlay;                       // lay_source(:,j), lev_source_dec(:,j)
+        const bool ok_inc = c_ok && has_lev && j >= 1 && j <= nlay; // lev_source_inc(:,j-1)
+        double a0, a1;
+        int it = planck_index(m, tl, a0, a1);
+        const PlT *tl_p = spl + (max(it, 1) - 1);
+        const Real l0 = (Real)div_const(a0, m.pi, m.r_pi), l1 = (Real)div_const(a1, m.pi, m.r_pi);
+        const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
+        char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
+        // g-points in batches of GB: all table reads of a batch are issued before its arithmetic and its
+        // stores, so that a batch is GB independent chains instead of one serial LDS -> F2F -> FMA -> STG chain
+        constexpr int GB = 4;
+        // (rows of g-points beyond ngpt exist in the shared table and hold zeros: reads need no clamp; a whole
+        //  g-group -- the usual case -- needs no per-g-point store predicate either)
+        if (has_lev) {
+            it = planck_index(m, tv, a0, a1);
+            const PlT *tv_p = spl + (max(it, 1) - 1);
+            const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
+            char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
+            char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
+            auto gloop = [&](auto full) {
+                constexpr bool FULL = decltype(full)::value;
+                const int ngl = FULL ? kGP : ng;
+                const PlT *tlp = tl_p, *tvp = tv_p;
+                for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_, tvp += GB * S_) {
+                    Real pl0[GB], pl1[GB], pv0[GB], pv1[GB];
+#pragma unroll
+                    for (int k = 0; k < GB; ++k) { rows2(tlp + k * S_, pl0[k], pl1[k]); rows2(tvp + k * S_, pv0[k], pv1[k]); }
+                    Real vl[GB], vv[GB];
+#pragma unroll
+                    for (int k = 0; k < GB; ++k) {
+                        vl[k] = fma_(l1, pl1[k], mul_(l0, pl0[k]));
+                        vv[k] = fma_(v1, pv1[k], mul_(v0, pv0[k]));      // B(tlev(:,j))
+                    }
+#pragma unroll
+                    for (int k = 0; k < GB; ++k) {
+                        const bool gk = FULL || gq + k < ng;
+                        stcs_if(reinterpret_cast<Real *>(p_lay), vl[k], ok_lay && gk);
+                        stcs_if(reinterpret_cast<Real *>(p_dec), vv[k], ok_lay && gk);            // lev_source_dec(:,j)   :424
+                        stcs_if(reinterpret_cast<Real *>(p_inc), vv[k], ok_inc && gk);            // lev_source_inc(:,j-1) :423
+                        p_lay += plane_b; p_dec += plane_b; p_inc += plane_b;
+                    }
+                }
+            };
+            if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
+        } else {
+            auto gloop = [&](auto full) {
+                constexpr bool FULL = decltype(full)::value;
+                const int ngl = FULL ? kGP : ng;
+                const PlT *tlp = tl_p;
+                for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_) {
+                    Real pl0[GB], pl1[GB];
+#pragma unroll
+                    for (int k = 0; k < GB; ++k) rows2(tlp + k * S_, pl0[k], pl1[k]);
+#pragma unroll
+                    for (int k = 0; k < GB; ++k) {
+                        const Real vl = fma_(l1, pl1[k], mul_(l0, pl0[k]));
+                        stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && (FULL || gq + k < ng));
+                        p_lay += plane_b;
+                    }
+                }
+            };
+            if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
+        }
+    };
     int iw = -1;                                               // index-role id of this warp (-1: another role)
     // ================================ helper warpgroup ================================
     if (warp >= kQNCW + kQNI) {
@@ -260,7 +369,6 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             return;
         }
         const int pw = hw - 1;
-        const int ng = min(kGP, ngpt - g0);
         if (SW) {
             // ---- source warps (SW): lanes = columns.  toa_src(:, g) = solar_irradiance(g) :468-472 and the g = 0
             //      plane :460, written with plain 256-byte row stores: it does not have to pass through the TMA unit ----
@@ -279,103 +387,19 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             }
             return;
         }
-        // ---- Planck warps (LW): lanes = columns, a unit is one level of one tile ----
+        // ---- Planck warps (LW) ----
         {
             if (ECCKD_DBG(64)) return;
-            const int S_ = pl_pitch;
-            auto rows2 = [](const PlT *p, Real &x, Real &y) {          // table rows r and r + 1 of one g-point
-                if constexpr (sizeof(Real) == 8) { x = p[0]; y = p[1]; }
-                else { const float2 v = *p; x = v.x; y = v.y; }
-            };
-            const bool has_lev = a.tlev != nullptr;
-            const int nlevu = has_lev ? nlay + 1 : nlay;          // levels 0..nlay carry a value when tlev is present
-            const int nunit = nslot * nlevu;
-            auto place = [&](int u, int &j, long long &colp, bool &c_ok) {
-                const int ts = u / nlevu;
-                j = u - ts * nlevu;
-                const long long cc = (long long)((int)blockIdx.x + ts * (int)gridDim.x) * kQCols + lane;
-                c_ok = cc < ncol;
-                colp = min(cc, (long long)ncol - 1);
-            };
-            // software pipeline: the temperatures of the next unit are fetched before the g-loop of the current one
-            auto fetch = [&](int u, double &tl, double &tv) {
-                int j; long long colp; bool c_ok;
-                place(u, j, colp, c_ok);
-                tl = (double)a.tlay[colp + (long long)ncol * min(j, nlay - 1)];
-                tv = 0.0;
-                if (has_lev) tv = (double)a.tlev[colp + (long long)ncol * min(j, nlay)];
-            };
+            // software pipeline: the next unit is claimed and its temperatures fetched before the g-loop of the current one
             double tl_n = 0.0, tv_n = 0.0;
-            if (pw < nunit) fetch(pw, tl_n, tv_n);
-            const size_t plane_b = plane * sizeof(Real);
-            for (int u = pw; u < nunit; u += NPW) {
-                int j; long long colp; bool c_ok;
-                place(u, j, colp, c_ok);
-                const bool ok_lay = c_ok && j < nlay;                       // lay_source(:,j), lev_source_dec(:,j)
-                const bool ok_inc = c_ok && has_lev && j >= 1 && j <= nlay; // lev_source_inc(:,j-1)
+            int u = claim_unit();
+            if (u < nunit) planck_fetch(u, tl_n, tv_n);
+            while (u < nunit) {
+                const int un = claim_unit();
                 const double tl = tl_n, tv = tv_n;
-                if (u + NPW < nunit) fetch(u + NPW, tl_n, tv_n);
-                double a0, a1;
-                int it = planck_index(m, tl, a0, a1);
-                const PlT *tl_p = spl + (max(it, 1) - 1);
-                const Real l0 = (Real)div_const(a0, m.pi, m.r_pi), l1 = (Real)div_const(a1, m.pi, m.r_pi);
-                const size_t off = (size_t)colp + pitch * (size_t)j + plane * (size_t)g0;
-                char *p_lay = reinterpret_cast<char *>(a.out[1] + off);
-                // g-points in batches of GB: all table reads of a batch are issued before its arithmetic and its
-                // stores, so that a batch is GB independent chains instead of one serial LDS -> F2F -> FMA -> STG chain
-                constexpr int GB = 4;
-                // (rows of g-points beyond ngpt exist in the shared table and hold zeros: reads need no clamp; a whole
-                //  g-group -- the usual case -- needs no per-g-point store predicate either)
-                if (has_lev) {
-                    it = planck_index(m, tv, a0, a1);
-                    const PlT *tv_p = spl + (max(it, 1) - 1);
-                    const Real v0 = (Real)div_const(a0, m.pi, m.r_pi), v1 = (Real)div_const(a1, m.pi, m.r_pi);
-                    char *p_dec = reinterpret_cast<char *>(a.out[3] + off);
-                    char *p_inc = reinterpret_cast<char *>(a.out[2] + off) - pitch * sizeof(Real);   // only dereferenced when j >= 1
-                    auto gloop = [&](auto full) {
-                        constexpr bool FULL = decltype(full)::value;
-                        const int ngl = FULL ? kGP : ng;
-                        const PlT *tlp = tl_p, *tvp = tv_p;
-                        for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_, tvp += GB * S_) {
-                            Real pl0[GB], pl1[GB], pv0[GB], pv1[GB];
-#pragma unroll
-                            for (int k = 0; k < GB; ++k) { rows2(tlp + k * S_, pl0[k], pl1[k]); rows2(tvp + k * S_, pv0[k], pv1[k]); }
-                            Real vl[GB], vv[GB];
-#pragma unroll
-                            for (int k = 0; k < GB; ++k) {
-                                vl[k] = fma_(l1, pl1[k], mul_(l0, pl0[k]));
-                                vv[k] = fma_(v1, pv1[k], mul_(v0, pv0[k]));      // B(tlev(:,j))
-                            }
-#pragma unroll
-                            for (int k = 0; k < GB; ++k) {
-                                const bool gk = FULL || gq + k < ng;
-                                stcs_if(reinterpret_cast<Real *>(p_lay), vl[k], ok_lay && gk);
-                                stcs_if(reinterpret_cast<Real *>(p_dec), vv[k], ok_lay && gk);            // lev_source_dec(:,j)   :424
-                                stcs_if(reinterpret_cast<Real *>(p_inc), vv[k], ok_inc && gk);            // lev_source_inc(:,j-1) :423
-                                p_lay += plane_b; p_dec += plane_b; p_inc += plane_b;
-                            }
-                        }
-                    };
-                    if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
-                } else {
-                    auto gloop = [&](auto full) {
-                        constexpr bool FULL = decltype(full)::value;
-                        const int ngl = FULL ? kGP : ng;
-                        const PlT *tlp = tl_p;
-                        for (int gq = 0; gq < ngl; gq += GB, tlp += GB * S_) {
-                            Real pl0[GB], pl1[GB];
-#pragma unroll
-                            for (int k = 0; k < GB; ++k) rows2(tlp + k * S_, pl0[k], pl1[k]);
-#pragma unroll
-                            for (int k = 0; k < GB; ++k) {
-                                const Real vl = fma_(l1, pl1[k], mul_(l0, pl0[k]));
-                                stcs_if(reinterpret_cast<Real *>(p_lay), vl, ok_lay && (FULL || gq + k < ng));
-                                p_lay += plane_b;
-                            }
-                        }
-                    };
-                    if (ng == kGP) gloop(std::true_type{}); else gloop(std::false_type{});
-                }
+                if (un < nunit) planck_fetch(un, tl_n, tv_n);
+                planck_unit(u, tl, tv);
+                u = un;
             }
             if (a.out2d) {                                 // sfc_source(:, g) = B(tsfc)   :408-412
                 for (int ts = pw; ts < nslot; ts += NPW) {
@@ -437,6 +461,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         int pj = j, pts = ts;                                   // position kPF * NIW ahead of s
         for (int q2 = 0; q2 < kPF; ++q2) { pj += NIW; while (pj >= nlay) { pj -= nlay; ++pts; } }
         In nxt;
+        bool units_left = PHELP && !SW;
         if (iw < S) fetch(ts, j, nxt);
         for (int s = iw; s < Spad; s += NIW) {
             const In in = nxt;
@@ -495,7 +520,17 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                 if (cc < ncol)
                     for (int gq = 0; gq < min(kGP, ngpt - g0); ++gq) a.out2d[cc + (long long)ncol * (g0 + gq)] = (Real)m.solar[g0 + gq];
             }
-            if (n >= 1) mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap);
+            if (n >= 1) {
+                if constexpr (PHELP) {         // ring full: this warp is R positions ahead -- time for a Planck unit
+                    while (!mbar_test(&rec_empty[slot / L], (n - 1) & 1)) {
+                        const int u = units_left ? claim_unit() : nunit;
+                        if (u >= nunit) { units_left = false; mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap); break; }
+                        double tl, tv;
+                        planck_fetch(u, tl, tv);
+                        planck_unit(u, tl, tv);
+                    }
+                } else mbar_wait_relaxed(&rec_empty[slot / L], (n - 1) & 1, kIndexNap);
+            }
             RecT &rc = recs[slot];
             rc.c01[lane] = c01; rc.c23[lane] = c23; rc.lut[lane] = lutw; rc.aux[lane] = aux; rc.key[lane].k = key;
 #pragma unroll
@@ -504,6 +539,15 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
             if (lane == 0) mbar_arrive(&rec_full[slot / L]);
             j += NIW; while (j >= nlay) { j -= nlay; ++ts; }
             slot += NIW; while (slot >= R) { slot -= R; ++n; }
+        }
+        if constexpr (PHELP) {
+            while (units_left) {
+                const int u = claim_unit();
+                if (u >= nunit) break;
+                double tl, tv;
+                planck_fetch(u, tl, tv);
+                planck_unit(u, tl, tv);
+            }
         }
         return;
     }
@@ -769,7 +813,7 @@ template <typename Real> bool quad_eligible(const CallGases &cg, const KernelArg
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool STAGED = false, bool HIDX = false>
+template <typename Real, bool SW, int NV, bool LUT32, int R, int NBUF, int RC = 184, int RI = 64, int RH = 64, bool ZERO_BY_TMA = false, int L = 1, int NX = 0, bool STAGED = false, bool HIDX = false, bool PHELP = false>
 static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const KernelArgs<Real> &a, const Real *mix, int sms, cudaStream_t s)
 {
     constexpr int NOUT = SW ? 2 : 1;
@@ -778,8 +822,8 @@ static cudaError_t launch_quad_t(const DevModel &m, const CallGases &cg, const K
     for (int o = 0; o < (SW ? 3 : 1); ++o)
         if (a.out[o] && !encode_quad_map<Real>(&maps.m[o], a.out[o], a.ncol, a.nlay, m.ngpt)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)NBUF * L * NOUT * TILEB + (SW ? 32 * 128 : 0) + sizeof(QRec<Real, NV, NX>) * R +
-                        (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * (m.nplanck + 1) * kGP);
-    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, STAGED, HIDX>;
+                        (2 * NBUF + 2 * R / L) * sizeof(unsigned long long) + (SW ? 0 : sizeof(float2) * (m.nplanck + 1) * kGP + 16);
+    auto kern = quad_kernel<Real, SW, NV, LUT32, R, NBUF, RC, RI, RH, ZERO_BY_TMA, L, NX, STAGED, HIDX, PHELP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
 #ifdef ECCKD_TUNE
@@ -847,7 +891,9 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         // staged refills: LW 2.05 -> 2.03 ms, fp32 LW 1.97 -> 1.91, fp32 SW 1.20 -> 1.13; fp64 SW 1.61 -> 1.65 (left off there)
         constexpr bool kStaged = !(SW && sizeof(Real) == 8);
         if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
-        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, kStaged>(m, cg, a, mix, sms, s);
+        // index warps helping with the Planck units: fp32 LW 1.85 -> 1.60 ms (there the three Planck warps set the pace);
+        // fp64 LW 2.03 -> 2.06 ms (there the compute warps do, and the helpers' extra instructions compete with them)
+        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
     }
     if (cg.nvar <= kQuadMaxVar) {      // up to three varying gases, all cached (fp32 LUT rows to make room)
         if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
