@@ -881,19 +881,24 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         }
     }
 #endif
-    // Production instantiations, as measured on B200 (tools/exp_quad.sh):
-    //   LW  look-up-table rows cached as fp32 (half the refill bytes and 32 registers less per compute thread); the
-    //       registers go to the Planck warps (128: batches of four g-points in flight) and the index warps (80)
-    //   SW  no Planck role: compute warps keep the LUT at full width (no conversions next to the ssa division), the
-    //       g = 0 plane leaves through the TMA unit
-    //                                          NV  LUT32   R NBUF   RC   RI   RH  ZERO_BY_TMA
+    // Production instantiations, as measured on B200 (DESIGN.md sections 4.2 and 5; every figure an A/B inside one gpurun call):
+    //   nvar <= 1   every table row cached at its own width.  LW: 168 registers per compute thread, 96 for the Planck
+    //               warps (batches of four g-points in flight), 80 for the index warps; record ring of 8 (131 KB of shared
+    //               memory, so that 124 KB of L1 are left for the table rows: 1.98 -> 1.97 ms).  SW: no Planck role, the
+    //               g = 0 plane leaves through the TMA unit, the compute warps take the registers nobody else needs
+    //   nvar <= 3   three varying gases cached, look-up-table rows cached as fp32 to make room
+    //   nvar 4..7   the other gases read uncached every layer
+    //                                          NV  LUT32   R NBUF   RC   RI   RH  ZERO_BY_TMA  L NX STAGED HIDX PHELP
     if (cg.nvar <= 1) {
-        // staged refills: LW 2.05 -> 2.03 ms, fp32 LW 1.97 -> 1.91, fp32 SW 1.20 -> 1.13; fp64 SW 1.61 -> 1.65 (left off there)
-        constexpr bool kStaged = !(SW && sizeof(Real) == 8);
-        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, 184, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
+        // staged refills: LW 2.05 -> 2.03 ms, fp32 LW 1.97 -> 1.91, fp32 SW 1.20 -> 1.13; fp64 SW 1.61 -> 1.65 with 184 registers
+        // per compute thread, 1.55 -> 1.54 with 192
+        constexpr bool kStaged = true;
+        // SW leaves 16 registers per thread unclaimed at 184 / 64 / 64: the fp64 compute warps take them (1.58 -> 1.55 ms; fp32 loses 2 %)
+        constexpr int kSwRc = sizeof(Real) == 8 ? 192 : 184;
+        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
         // index warps helping with the Planck units: fp32 LW 1.85 -> 1.60 ms (there the three Planck warps set the pace);
         // fp64 LW 2.03 -> 2.06 ms (there the compute warps do, and the helpers' extra instructions compete with them)
-        else return launch_quad_t<Real, SW, 1, false, 16, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, 1, false, 8, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
     }
     if (cg.nvar <= kQuadMaxVar) {      // up to three varying gases, all cached (fp32 LUT rows to make room)
         if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
