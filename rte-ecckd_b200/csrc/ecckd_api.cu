@@ -563,12 +563,10 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
     }
     if (k64.size() >= (size_t)1 << 30) { set_err(err, "ecckd_model_create: tables too large"); return ECCKD_ERR_ARG; }
     std::vector<float> k32(k64.size());
-    bool fp32_normal = true;    // no fp32 subnormals: the walking kernels may widen table rows with integer operations
     for (size_t q = 0; q < k64.size(); ++q) {
         k32[q] = (float)k64[q];
         if ((double)k32[q] != k64[q]) M->fp32_exact = false;
         if (k64[q] < 0.0) M->tables_nonneg = false;
-        if (k32[q] != 0.0f && std::fabs(k32[q]) < 1.17549435e-38f) fp32_normal = false;
     }
     std::vector<double> p64;
     std::vector<float> p32;
@@ -593,7 +591,7 @@ int ecckd_model_create(const ecckd_host_tables *t, int ndev, const int *devices,
             if (sidx < 0) { sidx = nslot++; slot_off.push_back(M->table_off[i]); }
             M->slot[i] = sidx;
         }
-        M->walk_model = M->tables_nonneg && M->fp32_exact && fp32_normal && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP &&
+        M->walk_model = M->tables_nonneg && M->fp32_exact && nlut <= 1 && nslot <= kMaxBil && t->npress <= kNPP && t->ntemp <= kNTP &&
                         M->nplanck <= 256;   // the per-block shared-memory copy of the Planck LUT must fit beside records and tiles
         if (M->walk_model) {
             const int ngroups = (t->ngpt + kGP - 1) / kGP, ng = t->ngpt, np = t->npress, nt = t->ntemp;
