@@ -1,6 +1,10 @@
 # Tuning-build experiments for the quad kernel.  Build first:  make -C rte-ecckd_b200/csrc -B EXTRA=-DECCKD_TUNE
-#   ECCKD_QUAD_VARIANT=<n>  alternative instantiation (register split, LUT width, ring sizes ...: the table next to
-#                           ECCKD_QUAD_VARIANT in csrc/ecckd_quad.cu)
+#   ECCKD_QUAD_VARIANT=<n>  alternative instantiation (register split, LUT width, ring sizes, staged refills ...: the table
+#                           next to ECCKD_QUAD_VARIANT in csrc/ecckd_quad.cu).  NOTE: the run-time experiment switches cost the
+#                           tuning build registers (it spills where the production build does not): use it to find out WHERE
+#                           time goes; decide between variants with two PRODUCTION builds (a -D macro around the
+#                           instantiation) copied to the box and timed by bench.py inside one gpurun call
+#   ECCKD_CARVEOUT=<pct>    preferred shared-memory carve-out (100: smallest L1), ECCKD_VERBOSE=1 prints the shared-memory size
 #   ECCKD_DBG=<bits>        timing experiments, results are WRONG: 1 no TMA stores, 2 index warps idle after the first ring
 #                           fill, 4 no arithmetic, 8 no cache refills, 16 no staging stores / proxy fence, 64 no Planck warps,
 #                           128 Planck warps only
