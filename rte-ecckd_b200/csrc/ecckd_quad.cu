@@ -329,8 +329,9 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         if (hw == 0) {
             // ---- store warp: staging tiles -> cp.async.bulk.tensor stores ----
             if (lane == 0) {
-                // kStorePend bulk groups stay in flight: the tile of group n - kStorePend is handed back once group n has
-                // been issued, so the TMA unit always has the next store queued while it reads a tile out
+                // ECCKD_STORE_PEND bulk groups stay in flight: the tile of group n - pend is handed back once group n has been
+                // issued, so that the TMA unit has the next store queued while it reads a tile out (measured with 1 and 2:
+                // no change, the default waits for each group)
 #ifdef ECCKD_TUNE
                 const int pend = ECCKD_DBG(2048) ? 1 : ECCKD_DBG(4096) ? 2 : 0;
 #else
@@ -364,7 +365,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
                     if (s0 >= pend * L) { mbar_arrive(&tile_empty[rb]); if (++rb == NBUF) rb = 0; }
                     if (++b == NBUF) { b = 0; par ^= 1; }
                 }
-                tma_wait_all<0>();                       // (nobody waits for the last kStorePend tiles)
+                tma_wait_all<0>();                       // (nobody waits for the last tiles)
             }
             return;
         }
