@@ -485,6 +485,12 @@ def main() -> None:
             extras["generic_kernel"] = {"lw_ms": timed_call(lw, atm0, g0_, True, ecckd_b200.KERNEL_GENERIC), "sw_ms": timed_call(sw, atm0, g0_, False, ecckd_b200.KERNEL_GENERIC), "columns": nb0}
             extras["column_walk_kernel"] = {"lw_ms": timed_call(lw, atm0, g0_, True, ecckd_b200.KERNEL_COLWALK), "sw_ms": timed_call(sw, atm0, g0_, False, ecckd_b200.KERNEL_COLWALK),
                                             "columns": nb0, "note": "round-1 product kernel, now the fallback for column counts without a 16-byte layer pitch"}
+            atm_s = synthetic.make_atmosphere(nb0, NLAY, col0=col_base, device=dev, noise=0.0)
+            g_s = ecckd_b200.PreparedGases(atm_s.gas_list(), nb0, NLAY, np.float64, dev)
+            extras["smooth_atmosphere"] = {"lw_ms": timed_call(lw, atm_s, g_s, True), "sw_ms": timed_call(sw, atm_s, g_s, False), "columns": nb0,
+                                           "note": "the same block without the specification's cell-by-cell white noise (N(0, 5 K) on tlay, LogN(0, 0.5) on h2o): "
+                                                   "columns of a tile then share table rows and Planck-table banks; not the headline workload"}
+            del atm_s, g_s
             nodd = nb0 - 1
             atm_odd = synthetic.make_atmosphere(nodd, NLAY, col0=col_base, device=dev)
             g_odd = ecckd_b200.PreparedGases(atm_odd.gas_list(), nodd, NLAY, np.float64, dev)

@@ -88,8 +88,10 @@ def _copy_f(t: torch.Tensor, dtype) -> torch.Tensor:
 
 
 def make_atmosphere(ncol: int, nlay: int = 137, col0: int = 0, device="cpu", seed: int = SEED,
-                    ptop: float = 1.0, scalars: Dict[str, float] = None) -> Atmosphere:
-    """Columns col0 .. col0+ncol-1 of the synthetic GCM block."""
+                    ptop: float = 1.0, scalars: Dict[str, float] = None, noise: float = 1.0) -> Atmosphere:
+    """Columns col0 .. col0+ncol-1 of the synthetic GCM block.
+    `noise` scales the cell-by-cell white noise of the specification (N(0, 5 K) on tlay, LogN(0, 0.5) on h2o); 0 gives
+    profiles that vary only from column to column -- used by bench.py to show how much of the kernel time is the noise."""
     dev = torch.device(device)
     col = torch.arange(col0, col0 + ncol, dtype=torch.int64, device=dev)
     lev = torch.arange(0, nlay + 1, dtype=torch.int64, device=dev)
@@ -99,14 +101,14 @@ def make_atmosphere(ncol: int, nlay: int = 137, col0: int = 0, device="cpu", see
     plev_t = ptop + (psfc[None, :] - ptop) * s[:, None]
     play_t = 0.5 * (plev_t[1:, :] + plev_t[:-1, :])
     cell = col[None, :] * 4096 + lev[:nlay, None]
-    tlay_t = (_t_std(play_t) + 5.0 * _normal(seed, 2, cell)).clamp(160.0, 320.0)
+    tlay_t = (_t_std(play_t) + (5.0 * noise) * _normal(seed, 2, cell)).clamp(160.0, 320.0)
     tlev_t = torch.empty_like(plev_t)
     tlev_t[1:-1, :] = 0.5 * (tlay_t[1:, :] + tlay_t[:-1, :])
     tlev_t[0, :] = tlay_t[0, :]
     tlev_t[-1, :] = tlay_t[-1, :]
     tsfc = tlev_t[-1, :] + 2.0 * _normal(seed, 3, col)
     q0 = 1.0e-3 + (2.5e-2 - 1.0e-3) * _uniform(seed, 4, col)
-    h2o_t = (q0[None, :] * (play_t / psfc[None, :]) ** 3 * torch.exp(0.5 * _normal(seed, 5, cell))).clamp(1.0e-7, 4.0e-2)
+    h2o_t = (q0[None, :] * (play_t / psfc[None, :]) ** 3 * torch.exp((0.5 * noise) * _normal(seed, 5, cell))).clamp(1.0e-7, 4.0e-2)
     o3_t = 8.0e-6 * torch.exp(-0.5 * torch.log(play_t / 1000.0) ** 2) + 2.0e-8
     T = lambda x: x.contiguous().t()
     return Atmosphere(ncol, nlay, T(plev_t), T(tlay_t), T(tlev_t), tsfc.contiguous(), T(h2o_t), T(o3_t),
