@@ -589,7 +589,9 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
 
     // (re)load the register cache for corner offsets (pkoff, hkoff); every load is predicated on "this column's key
     // moved", so the four columns of the warp refill independently without divergence
+    bool first_fill = true;            // (ECCKD_DBG 8192: after the first fill the loads are issued with false predicates)
     auto refill_lut = [&](int hkoff, bool moved) {
+        if (ECCKD_DBG(8192) && !first_fill) moved = false;
         const bool pl = has_lut && moved;
         if (!ECCKD_DBG(8)) {
             ld_rows_if(kh[0], wlut + hkoff, pl);
@@ -597,9 +599,11 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         }
     };
     auto refill_mix = [&](int pkoff, bool moved) {
+        if (ECCKD_DBG(8192) && !first_fill) moved = false;
         if (!ECCKD_DBG(8)) ld_rows_if(km, wmix + pkoff, moved && has_mix);
     };
     auto refill_var = [&](int pkoff, bool moved) {
+        if (ECCKD_DBG(8192) && !first_fill) moved = false;
         if (!ECCKD_DBG(8)) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) ld_rows_if(kb[v], wvar[v] + pkoff, moved && v < nvar);
@@ -654,6 +658,7 @@ quad_kernel(const __grid_constant__ DevModel m, const __grid_constant__ CallGase
         load_rec(0, cur, true);
         refill_bil(cur.key.x & 0xffff, true);
         refill_lut(cur.key.y, true);
+        first_fill = false;
         nxt = cur;
         int slot = 0, rpar = 0, b = 0, tpar = 1;       // tpar: parity to wait for on tile_empty (the phase before the
                                                        // initial one counts as complete, so the first pass never blocks)

@@ -7,7 +7,7 @@
 #   ECCKD_CARVEOUT=<pct>    preferred shared-memory carve-out (100: smallest L1), ECCKD_VERBOSE=1 prints the shared-memory size
 #   ECCKD_DBG=<bits>        timing experiments, results are WRONG: 1 no TMA stores, 2 index warps idle after the first ring
 #                           fill, 4 no arithmetic, 8 no cache refills, 16 no staging stores / proxy fence, 64 no Planck warps,
-#                           128 Planck warps only
+#                           128 Planck warps only, 8192 refill loads issued with false predicates after the first fill
 #   ECCKD_BLOCKS=<n>        blocks per g-group (default: one per SM)
 # Compare only numbers from ONE run of this script: the B200 boxes of the pool differ by several per cent.
 for v in ${VARIANTS:-0 1 2}; do for b in lw sw; do echo -n "VAR=$v "; ECCKD_QUAD_VARIANT=$v timeout -s KILL 60 python tools/prof_one.py $b f64 walk 65536 6; done; done
