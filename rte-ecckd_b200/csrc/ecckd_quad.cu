@@ -888,7 +888,7 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
     }
 #endif
     // Production instantiations, as measured on B200 (DESIGN.md sections 4.2 and 5; every figure an A/B inside one gpurun call):
-    //   nvar <= 1   every table row cached at its own width.  LW: 168 registers per compute thread, 96 for the Planck
+    //   nvar <= 1   LW: 168 registers per compute thread, 96 for the Planck
     //               warps (batches of four g-points in flight), 80 for the index warps; record ring of 8 (131 KB of shared
     //               memory, so that 124 KB of L1 are left for the table rows: 1.98 -> 1.97 ms).  SW: no Planck role, the
     //               g = 0 plane leaves through the TMA unit, the compute warps take the registers nobody else needs
@@ -902,9 +902,14 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         // SW leaves 16 registers per thread unclaimed at 184 / 64 / 64: the fp64 compute warps take them (1.58 -> 1.55 ms; fp32 loses 2 %)
         constexpr int kSwRc = sizeof(Real) == 8 ? 192 : 184;
         if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
+        // fp64 LW caches the look-up-table rows as fp32 (exact: the tables are fp32 on file): half the bytes of the largest
+        // refill for 32 conversions per iteration, which the conversion unit can take now that the Planck warps do not use it
+        // (1.99 -> 1.89 ms; with other register splits -- 160/88/104, 152/96/112, 144/96/128 -- 1.96 - 2.03 ms).  SW keeps
+        // fp64 rows: its ssa divisions share that unit (1.56 -> 1.66 ms with fp32 rows)
+        constexpr bool kLwLut32 = sizeof(Real) == 8;
         // index warps helping with the Planck units: fp32 LW 1.85 -> 1.60 ms (there the three Planck warps set the pace);
         // fp64 LW 2.03 -> 2.06 ms (there the compute warps do, and the helpers' extra instructions compete with them)
-        else return launch_quad_t<Real, SW, 1, false, 8, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
+        else return launch_quad_t<Real, SW, 1, kLwLut32, 8, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
     }
     if (cg.nvar <= kQuadMaxVar) {      // up to three varying gases, all cached (fp32 LUT rows to make room)
         if constexpr (SW) return launch_quad_t<Real, SW, kQuadMaxVar, true, 16, 6, 184, 64, 64, true>(m, cg, a, mix, sms, s);
