@@ -901,12 +901,12 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         constexpr bool kStaged = true;
         // SW leaves 16 registers per thread unclaimed at 184 / 64 / 64: the fp64 compute warps take them (1.58 -> 1.55 ms; fp32 loses 2 %)
         constexpr int kSwRc = sizeof(Real) == 8 ? 192 : 184;
-        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
         // fp64 LW caches the look-up-table rows as fp32 (exact: the tables are fp32 on file): half the bytes of the largest
         // refill for 32 conversions per iteration, which the conversion unit can take now that the Planck warps do not use it
         // (1.99 -> 1.89 ms; with other register splits -- 160/88/104, 152/96/112, 144/96/128 -- 1.96 - 2.03 ms).  SW keeps
         // fp64 rows: its ssa divisions share that unit (1.56 -> 1.66 ms with fp32 rows)
         constexpr bool kLwLut32 = sizeof(Real) == 8;
+        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
         // index warps helping with the Planck units: fp32 LW 1.85 -> 1.60 ms (there the three Planck warps set the pace);
         // fp64 LW 2.03 -> 2.06 ms (there the compute warps do, and the helpers' extra instructions compete with them)
         else return launch_quad_t<Real, SW, 1, kLwLut32, 8, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
