@@ -10,7 +10,7 @@ for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m: cur = m.group(1); fn[cur] = []; continue
     if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line): fn[cur].append(re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line).rstrip())
-name = next(n for n in fn if "quad_kernelIdLb0ELi1ELb0E" in n)          # <double, LW, NV = 1, fp64 LUT ...>
+name = next(n for n in fn if "quad_kernelIdLb0ELi1ELb" in n)            # <double, LW, NV = 1, ...>: the production longwave kernel
 dem = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip() or name
 L = fn[name]
 pats = ["UTMASTG", "UTMACMDFLUSH", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "USETMAXREG", "FENCE.VIEW.ASYNC", "LDG.E.128.CONSTANT", "DFMA", "DMUL",
