@@ -76,6 +76,32 @@ def test_gpoint_count_sweep(key, ngpt, dtype, dev, ck_models):
         check(run_gpu(go, *inp, dtype, dev, kern), ref, TOL[dtype], f"{key} ngpt={ngpt} kernel={kern}")
 
 
+def regrid_planck(m, nplanck, t0, dt):
+    """The same longwave model with a Planck table of `nplanck` rows starting at t0 with spacing dt (resampled linearly
+    from the file's table, rounded to fp32 like the file's entries)."""
+    m = copy.deepcopy(m)
+    told, pold = m.temperature_planck, m.planck_function            # (n,), (n, ng)
+    tnew = t0 + dt * np.arange(nplanck)
+    pnew = np.stack([np.interp(tnew, told, pold[:, g]) for g in range(pold.shape[1])], axis=1)
+    m.temperature_planck = tnew.astype(np.float64)
+    m.planck_function = pnew.astype(np.float32).astype(np.float64)
+    return m
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("nplanck,t0,dt", [(2, 200.0, 60.0), (33, 180.0, 4.0), (256, 150.0, 0.75), (231, 260.0, 1.0)],
+                         ids=["2rows", "33rows", "256rows-max", "table-above-most-of-the-atmosphere"])
+def test_planck_table_size_sweep(nplanck, t0, dt, dtype, dev, ck_models):
+    """The block's shared-memory copy of the Planck table (pitch nplanck + 1, fp64 rows or fp32 pairs), extrapolation
+    above the last row and proportional scaling below the first (:278-284) -- against the oracle, on all three kernels."""
+    m = share_composite(regrid_planck(ck_models["lw_fsck"], nplanck, t0, dt))
+    go = ecckd_b200.GasOpticsEcckd.from_components(m)
+    inp = atm_numpy(synthetic.make_atmosphere(100, 61))
+    ref = run_oracle(oracle_for(m), m, *inp, dtype)
+    for kern in (ecckd_b200.KERNEL_QUAD, ecckd_b200.KERNEL_COLWALK, ecckd_b200.KERNEL_GENERIC):
+        check(run_gpu(go, *inp, dtype, dev, kern), ref, TOL[dtype], f"nplanck={nplanck} kernel={kern}")
+
+
 def _negative_entry(m):
     m = copy.deepcopy(m)
     tab = next(t for t, n in zip(m.absorption, m.gas) if n == "co2")
