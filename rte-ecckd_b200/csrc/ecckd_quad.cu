@@ -906,7 +906,10 @@ cudaError_t launch_quad(const DevModel &m, const CallGases &cg, const KernelArgs
         // (1.99 -> 1.89 ms; with other register splits -- 160/88/104, 152/96/112, 144/96/128 -- 1.96 - 2.03 ms).  SW keeps
         // fp64 rows: its ssa divisions share that unit (1.56 -> 1.66 ms with fp32 rows)
         constexpr bool kLwLut32 = sizeof(Real) == 8;
-        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, 1, 0, kStaged>(m, cg, a, mix, sms, s);
+        // fp32 SW (bound by issue slots) hands tiles and records over in groups of two layers: half the barrier operations
+        // per layer (1.125 -> 1.099 ms; fp32 LW 1.60 -> 1.65, fp64 no change: left at one)
+        constexpr int kSwL = sizeof(Real) == 4 ? 2 : 1;
+        if constexpr (SW) return launch_quad_t<Real, SW, 1, false, 16, 6, kSwRc, 64, 64, true, kSwL, 0, kStaged>(m, cg, a, mix, sms, s);
         // index warps helping with the Planck units: fp32 LW 1.85 -> 1.60 ms (there the three Planck warps set the pace);
         // fp64 LW 2.03 -> 2.06 ms (there the compute warps do, and the helpers' extra instructions compete with them)
         else return launch_quad_t<Real, SW, 1, kLwLut32, 8, 6, 168, 80, 96, false, 1, 0, kStaged, false, sizeof(Real) == 4>(m, cg, a, mix, sms, s);
