@@ -499,6 +499,17 @@ def main() -> None:
             del atm_odd, g_odd
         except Exception as exc:
             extras["kernels_error"] = str(exc)
+        try:      # configs[2]: the other longwave file at the same block size (36 g-points: a full group of 32 and a group of 4)
+            lw36 = ecckd_b200.GasOpticsEcckd.load(os.path.join(DATA, "ecckd-1.2_lw_ckd-definition_climate_rrtmgp-tol0.061.nc"))
+            atm36, g36 = blocks[0][0], blocks[0][1]
+            ms36, ng36 = timed_call(lw36, atm36, g36, True), lw36.get_ngpt()
+            extras["lw_rrtmgp-tol0.061"] = {"lw_ms": ms36, "ngpt": ng36, "columns": atm36.ncol,
+                                            "gptl_per_s": atm36.ncol * NLAY * ng36 / (ms36 * 1e-3),
+                                            "frac_of_hbm_peak": algorithmic_bytes(atm36.ncol, NLAY, ng36, True, 8) / (ms36 * 1e-3) / 1e9 / peak,
+                                            "note": "the g-points run as groups of 32 (grid.y): the second group carries 4 of 32"}
+            del lw36
+        except Exception as exc:
+            extras["lw_rrtmgp_error"] = str(exc)
         try:
             extras["rfmip"] = rfmip_latencies(dev)
         except Exception as exc:
