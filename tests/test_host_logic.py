@@ -57,6 +57,19 @@ def test_synthetic_atmosphere_is_physical_and_toa_first():
     assert [n for n, _ in atm.gas_list()] == list(synthetic.GAS_ORDER)
 
 
+def test_synthetic_noise_scale_only_touches_the_noisy_fields():
+    """`noise` scales the cell-by-cell white noise of SURVEY 8d config 4 (tlay, h2o); the default is the specification,
+    0 removes it (bench.py's smooth_atmosphere extra) and leaves pressures, ozone and the scalars alone."""
+    a, b = synthetic.make_atmosphere(12, 137), synthetic.make_atmosphere(12, 137, noise=0.0)
+    assert torch.equal(a.plev, b.plev) and torch.equal(a.o3, b.o3) and a.scalars == b.scalars
+    assert not torch.equal(a.tlay, b.tlay) and not torch.equal(a.h2o, b.h2o)
+    # without noise a column's temperature is a smooth function of pressure: neighbouring layers differ by < 10 K
+    # (with the N(0, 5 K) noise of the specification by more than 15 K somewhere in 12 x 137 cells)
+    step = lambda t: float((t[:, 1:] - t[:, :-1]).abs().max())
+    assert step(b.tlay) < 10.0 < 15.0 < step(a.tlay)
+    assert torch.equal(synthetic.make_atmosphere(12, 137, noise=1.0).tlay, a.tlay)
+
+
 def test_synthetic_columns_do_not_depend_on_the_shard():
     full = synthetic.make_atmosphere(100, 60)
     for world in (2, 3, 8):
